@@ -1,0 +1,121 @@
+/*
+ * pv_koala_b200.h -- C ABI of libpv_koala_b200.so, a B200-native drop-in for the per-frame noise-suppression path of
+ * Picovoice Koala (`pv_koala_process`).  Plain C: opaque handles, plain pointers and sizes, no CUDA or torch types.
+ *
+ * Part 1 re-declares, with identical names, signatures, status codes and ownership rules, every symbol the reference
+ * engine exports (`nm -D lib/linux/x86_64/libpv_koala.so`: 18 functions) so that the reference's own bindings
+ * (binding/python/_koala.py:154-222, demo/c/koala_demo_file.c:265-333) bind to this library unmodified.  Each
+ * declaration cites the reference interface it replaces (paths relative to /root/reference).
+ * Part 2 is an additive batched extension (not in the reference): many independent streams per call, host or device
+ * buffers.  See INTEGRATION.md for the binding stubs.
+ */
+#ifndef PV_KOALA_B200_H
+#define PV_KOALA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ Part 1: the reference surface ---------------- */
+
+/* include/picovoice.h:41-54 -- same enumerators, same values */
+typedef enum {
+    PV_STATUS_SUCCESS = 0,
+    PV_STATUS_OUT_OF_MEMORY,
+    PV_STATUS_IO_ERROR,
+    PV_STATUS_INVALID_ARGUMENT,
+    PV_STATUS_STOP_ITERATION,
+    PV_STATUS_KEY_ERROR,
+    PV_STATUS_INVALID_STATE,
+    PV_STATUS_RUNTIME_ERROR,
+    PV_STATUS_ACTIVATION_ERROR,
+    PV_STATUS_ACTIVATION_LIMIT_REACHED,
+    PV_STATUS_ACTIVATION_THROTTLED,
+    PV_STATUS_ACTIVATION_REFUSED
+} pv_status_t;
+
+/* include/picovoice.h:33-36 -- 16000 */
+PV_API int32_t pv_sample_rate(void);
+/* include/picovoice.h:56-62 -- "SUCCESS" ... "ACTIVATION_REFUSED"; NULL outside the enum (observed on the reference .so) */
+PV_API const char *pv_status_to_string(pv_status_t status);
+/* include/picovoice.h:64-79 -- per-thread stack of the last failure, readable once; INVALID_STATE + depth 0 if none pending */
+PV_API pv_status_t pv_get_error_stack(char ***message_stack, int32_t *message_stack_depth);
+/* include/picovoice.h:81-86 */
+PV_API void pv_free_error_stack(char **message_stack);
+
+/* include/pv_koala.h:27-35 -- one handle == one 16 kHz mono stream with its analysis tail, OLA tail and recurrent state */
+typedef struct pv_koala pv_koala_t;
+
+/* include/pv_koala.h:37-56.  access_key: syntax-checked only (no licence server).  model_path: a koala_b200 .kpv file.
+ * device: "best" | "gpu" | "gpu:K" (B200 only); "cpu" / "cpu:N" parse but fail with PV_STATUS_RUNTIME_ERROR -- this
+ * library has no CPU engine by design. */
+PV_API pv_status_t pv_koala_init(const char *access_key, const char *model_path, const char *device, pv_koala_t **object);
+/* include/pv_koala.h:58-63 -- NULL is a no-op */
+PV_API void pv_koala_delete(pv_koala_t *object);
+/* include/pv_koala.h:65-80 -- pcm and enhanced_pcm: caller-allocated host buffers of pv_koala_frame_length() samples */
+PV_API pv_status_t pv_koala_process(pv_koala_t *object, const int16_t *pcm, int16_t *enhanced_pcm);
+/* include/pv_koala.h:82-90 */
+PV_API pv_status_t pv_koala_reset(pv_koala_t *object);
+/* include/pv_koala.h:92-100 -- 256 */
+PV_API pv_status_t pv_koala_delay_sample(const pv_koala_t *object, int32_t *delay_sample);
+/* include/pv_koala.h:102-107 -- 256 */
+PV_API int32_t pv_koala_frame_length(void);
+/* include/pv_koala.h:109-114 */
+PV_API const char *pv_koala_version(void);
+/* include/pv_koala.h:116-128 -- entries "gpu:K - <name>" for every compute-capability-10.x device */
+PV_API pv_status_t pv_koala_list_hardware_devices(char ***hardware_devices, int32_t *num_hardware_devices);
+/* include/pv_koala.h:130-138 */
+PV_API void pv_koala_free_hardware_devices(char **hardware_devices, int32_t num_hardware_devices);
+
+/* exported by the reference binary but absent from its headers; binding/python/_koala.py:156-160 calls pv_set_sdk */
+PV_API void pv_set_sdk(const char *sdk);
+PV_API const char *pv_get_sdk(void);
+PV_API void pv_free(void *ptr);
+PV_API void pv_log_enable(void);
+PV_API void pv_log_disable(void);
+
+/* ------------------------------------------------------------------ Part 2: batched extension -------------------- */
+
+/* B independent streams resident on one GPU; stream s keeps the same state a pv_koala_t would. */
+typedef struct pv_koala_batch pv_koala_batch_t;
+
+/* precision: "bf16" (tcgen05 tensor-core mask estimator, default when NULL) or "fp32" (CUDA-core mask estimator). */
+PV_API pv_status_t pv_koala_batch_init(const char *model_path, const char *device, int32_t num_streams, const char *precision,
+                                       pv_koala_batch_t **object);
+PV_API void pv_koala_batch_delete(pv_koala_batch_t *object);
+
+/* pcm / enhanced_pcm: [num_streams][num_frames][256] int16, both host or both device memory (detected).  Frame t of
+ * every stream is one step of the hot path; state carries across calls exactly as across pv_koala_process calls.
+ * Host buffers: copies + compute + copy back, returns when enhanced_pcm is valid.  Device buffers: synchronous too. */
+PV_API pv_status_t pv_koala_batch_process(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm, int32_t num_frames);
+
+/* Device buffers only, enqueue-only: frame t of stream s at base + s * stream_stride + t * 256 samples (16-byte aligned,
+ * stride % 8 == 0).  cuda_stream: a cudaStream_t (NULL = the handle's own stream).  Pair with pv_koala_batch_synchronize. */
+PV_API pv_status_t pv_koala_batch_process_async(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,
+                                                int32_t num_frames, int64_t stream_stride, void *cuda_stream);
+PV_API pv_status_t pv_koala_batch_synchronize(pv_koala_batch_t *object);
+
+/* stream_ids == NULL resets every stream (pv_koala_reset semantics per stream). */
+PV_API pv_status_t pv_koala_batch_reset(pv_koala_batch_t *object, const int32_t *stream_ids, int32_t num_ids);
+PV_API pv_status_t pv_koala_batch_num_streams(const pv_koala_batch_t *object, int32_t *num_streams);
+PV_API pv_status_t pv_koala_batch_delay_sample(const pv_koala_batch_t *object, int32_t *delay_sample);
+/* kernels launched so far by this handle (bench.py's gpu_launches) */
+PV_API pv_status_t pv_koala_batch_kernel_launches(const pv_koala_batch_t *object, int64_t *launches);
+/* Per-kernel-class CUDA-event timing on the launching stream (classes: 0 analysis/STFT, 1 encoder GEMM, 2 GRU layer,
+ * 3 decoder GEMM, 4 synthesis/iSTFT).  Enable, run steps, then read: read synchronises, returns summed milliseconds and
+ * launch counts per class since the previous read.  Off by default (events perturb back-to-back launches). */
+PV_API pv_status_t pv_koala_batch_profile(pv_koala_batch_t *object, int32_t enable);
+PV_API pv_status_t pv_koala_batch_profile_read(pv_koala_batch_t *object, double *ms_per_class, int64_t *launches_per_class,
+                                               int32_t num_classes);
+/* test hook: copy an internal tensor of the last step to the host: "feat" "spec" "mask" "e" "h0".."h7" "ola" "tail" */
+PV_API pv_status_t pv_koala_batch_debug_read(pv_koala_batch_t *object, const char *name, void *dst, int64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PV_KOALA_B200_H */

@@ -1,0 +1,430 @@
+// koala_b200 -- Engine implementation: state layout in HBM, model upload, per-step launch sequence.
+//
+// Per-stream state rows (all zero after reset, pv_koala.h:82-90):
+//   tail [Bp][256] int16   previous input frame (analysis overlap)
+//   ola  [Bp][256] fp32    second half of the previous synthesis frame
+//   h    [2][L][Bp][H] fp32  recurrent state, ping-pong by step parity (every unit tile reads all of h(t-1))
+//   hb   [2][L][Bp][H] bf16  the same state rounded to bf16 = GEMM operand of the tensor-core path
+// Scratch per step: feat [Bp][256] (fp32 | bf16), spec [Bp][512] fp32, e [Bp][H], mask [Bp][256] fp32.
+// Bp = B rounded up to 128 so that every GEMM tile is full; padding rows stay zero-input and are never copied out.
+#include "engine.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "koala_common.cuh"
+#include "masknet_fp32.cuh"
+#include "masknet_tc.cuh"
+#include "stft_kernels.cuh"
+
+namespace koala {
+
+// ------------------------------------------------------------------------------------------------ model file
+static uint32_t crc32_bytes(const uint8_t *p, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int j = 0; j < 8; j++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        init = true;
+    }
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
+
+Status load_model_file(const char *path, ModelHost *out, std::vector<std::string> *errors) {
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        errors->push_back(std::string("Failed to open file `") + path + "`.");
+        return kIoError;
+    }
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> blob(n > 0 ? n : 0);
+    const bool ok = n > 0 && fread(blob.data(), 1, n, f) == (size_t) n;
+    fclose(f);
+    if (!ok) {
+        errors->push_back(std::string("Failed to read file `") + path + "`.");
+        return kIoError;
+    }
+    if (n < 48 || memcmp(blob.data(), "koala_b200\0\0", 12) != 0) {
+        // the reference's own blob starts with "koala3.0.0" (SURVEY.md F6); it is a different product's format
+        char product[13] = {0};
+        for (int i = 0; i < 12 && i < n; i++) product[i] = (blob[i] >= 32 && blob[i] < 127) ? (char) blob[i] : '.';
+        errors->push_back(std::string("Model file product is `") + product + "` but library product is `koala_b200`.");
+        return kInvalidArgument;
+    }
+    uint32_t hd[8];
+    memcpy(hd, blob.data() + 12, 32);
+    if (hd[0] != 1 || hd[1] != (uint32_t) kNfft || hd[2] != (uint32_t) kFrame || hd[3] != (uint32_t) kBins || hd[6] != 1 ||
+        hd[5] < 1 || hd[5] > (uint32_t) kMaxLayers || hd[4] < 64 || hd[4] > 4096 || hd[4] % 64 != 0) {
+        errors->push_back("Model file belongs to a different version of the library.");
+        return kInvalidArgument;
+    }
+    const size_t H = hd[4], L = hd[5];
+    const size_t need = 44 + 2 * H * kBins + 4 * H + L * (2 * 2 * 3 * H * H + 2 * 4 * 3 * H) + 2 * kBins * H + 4 * kBins + 4;
+    uint32_t crc;
+    memcpy(&crc, blob.data() + n - 4, 4);
+    if ((size_t) n != need || crc != crc32_bytes(blob.data(), n - 4)) {
+        errors->push_back("Model file is corrupt (size or checksum mismatch).");
+        return kInvalidArgument;
+    }
+    out->hidden = (int) H;
+    out->layers = (int) L;
+    const uint8_t *p = blob.data() + 44;
+    auto take16 = [&](std::vector<uint16_t> &v, size_t cnt) { v.resize(cnt); memcpy(v.data(), p, 2 * cnt); p += 2 * cnt; };
+    auto take32 = [&](std::vector<float> &v, size_t cnt) { v.resize(cnt); memcpy(v.data(), p, 4 * cnt); p += 4 * cnt; };
+    take16(out->enc_w, H * kBins);
+    take32(out->enc_b, H);
+    out->wih.resize(L); out->whh.resize(L); out->bih.resize(L); out->bhh.resize(L);
+    for (size_t l = 0; l < L; l++) {
+        take16(out->wih[l], 3 * H * H);
+        take16(out->whh[l], 3 * H * H);
+        take32(out->bih[l], 3 * H);
+        take32(out->bhh[l], 3 * H);
+    }
+    take16(out->dec_w, kBins * H);
+    take32(out->dec_b, kBins);
+    return kSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct Engine::Impl {
+    cudaStream_t stream = nullptr;
+    int H = 0, L = 0;
+    int parity = 0;   // h[parity] holds h(t-1)
+    // model
+    __nv_bfloat16 *enc_w = nullptr, *dec_w = nullptr, *wih[kMaxLayers] = {}, *whh[kMaxLayers] = {};
+    float *enc_b = nullptr, *dec_b = nullptr, *bih[kMaxLayers] = {}, *bhh[kMaxLayers] = {};
+    float *tables = nullptr;
+    // state
+    int16_t *tail = nullptr;
+    float *ola = nullptr;
+    float *h[2] = {};            // [L][Bp][H]
+    __nv_bfloat16 *hb[2] = {};   // [L][Bp][H]   (bf16 path)
+    // scratch
+    void *feat = nullptr;        // fp32 | bf16 [Bp][256]
+    float *spec = nullptr;       // [Bp][512]
+    void *e = nullptr;           // fp32 | bf16 [Bp][H]
+    float *mask = nullptr;       // [Bp][256]
+    // staging for host-buffer calls
+    int16_t *d_in = nullptr, *d_out = nullptr;
+    size_t staging_frames = 0;
+    TcPlan *tc = nullptr;        // tensor maps + packed weights of the tcgen05 path
+    KernelProfiler *prof = nullptr;
+    std::vector<void *> allocs;
+};
+
+#define KCHECK(expr)                                                                                      \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            if (errors) errors->push_back(std::string(#expr) + " failed: " + cudaGetErrorString(e__));    \
+            return e__ == cudaErrorMemoryAllocation ? kOutOfMemory : kRuntimeError;                       \
+        }                                                                                                 \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(std::vector<void *> &allocs, T **ptr, size_t count, bool zero = true) {
+    cudaError_t e = cudaMalloc((void **) ptr, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    allocs.push_back(*ptr);
+    return zero ? cudaMemset(*ptr, 0, count * sizeof(T)) : cudaSuccess;
+}
+
+template <typename T, typename S>
+static cudaError_t upload(std::vector<void *> &allocs, T **ptr, const std::vector<S> &src) {
+    static_assert(sizeof(T) == sizeof(S), "element size");
+    cudaError_t e = dev_alloc(allocs, ptr, src.size(), false);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*ptr, src.data(), src.size() * sizeof(S), cudaMemcpyHostToDevice);
+}
+
+Status Engine::create(const ModelHost &model, int device, int num_streams, int precision, Engine **out,
+                      std::vector<std::string> *errors) {
+    if (num_streams < 1 || (precision != kFp32 && precision != kBf16)) {
+        errors->push_back("Invalid number of streams or precision.");
+        return kInvalidArgument;
+    }
+    KCHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    KCHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        // the reference probes its device with `compatibility_test_kernel` and fails the same way
+        errors->push_back("Selected GPU device is incompatible with the library (needs compute capability 10.x).");
+        return kRuntimeError;
+    }
+    Engine *eng = new Engine();
+    Impl *p = eng->p_ = new Impl();
+    eng->n_ = num_streams;
+    eng->npad_ = (num_streams + 127) / 128 * 128;
+    eng->device_ = device;
+    eng->precision_ = precision;
+    const size_t Bp = eng->npad_, H = model.hidden, L = model.layers;
+    p->H = (int) H;
+    p->L = (int) L;
+    Status st = [&]() -> Status {
+        KCHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        KCHECK(upload(p->allocs, &p->enc_w, model.enc_w));
+        KCHECK(upload(p->allocs, &p->enc_b, model.enc_b));
+        KCHECK(upload(p->allocs, &p->dec_w, model.dec_w));
+        KCHECK(upload(p->allocs, &p->dec_b, model.dec_b));
+        for (size_t l = 0; l < L; l++) {
+            KCHECK(upload(p->allocs, &p->wih[l], model.wih[l]));
+            KCHECK(upload(p->allocs, &p->whh[l], model.whh[l]));
+            KCHECK(upload(p->allocs, &p->bih[l], model.bih[l]));
+            KCHECK(upload(p->allocs, &p->bhh[l], model.bhh[l]));
+        }
+        std::vector<float> tab(kTableBytes / 4);
+        for (int i = 0; i < kNfft; i++) tab[i] = (float) sin(M_PI * (double) i / kNfft);
+        for (int k = 0; k < kNfft / 2; k++) {
+            const double a = -2.0 * M_PI * (double) k / kNfft;
+            tab[kNfft + 2 * k] = (float) cos(a);
+            tab[kNfft + 2 * k + 1] = (float) sin(a);
+        }
+        KCHECK(upload(p->allocs, &p->tables, tab));
+        KCHECK(dev_alloc(p->allocs, &p->tail, Bp * kFrame));
+        KCHECK(dev_alloc(p->allocs, &p->ola, Bp * kFrame));
+        KCHECK(dev_alloc(p->allocs, &p->spec, Bp * kNfft));
+        KCHECK(dev_alloc(p->allocs, &p->mask, Bp * kBins));
+        for (int i = 0; i < 2; i++) KCHECK(dev_alloc(p->allocs, &p->h[i], L * Bp * H));
+        if (precision == kFp32) {
+            KCHECK(dev_alloc(p->allocs, (float **) &p->feat, Bp * kBins));
+            KCHECK(dev_alloc(p->allocs, (float **) &p->e, Bp * H));
+        } else {
+            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->feat, Bp * kBins));
+            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->e, Bp * H));
+            for (int i = 0; i < 2; i++) KCHECK(dev_alloc(p->allocs, &p->hb[i], L * Bp * H));
+            TcModel tm;
+            tm.H = (int) H; tm.L = (int) L; tm.Bp = (int) Bp;
+            tm.enc_w = p->enc_w; tm.dec_w = p->dec_w; tm.enc_b = p->enc_b; tm.dec_b = p->dec_b;
+            for (size_t l = 0; l < L; l++) { tm.wih[l] = p->wih[l]; tm.whh[l] = p->whh[l]; tm.bih[l] = p->bih[l]; tm.bhh[l] = p->bhh[l]; }
+            tm.feat = (__nv_bfloat16 *) p->feat; tm.e = (__nv_bfloat16 *) p->e; tm.mask = p->mask;
+            for (int i = 0; i < 2; i++) { tm.h[i] = p->h[i]; tm.hb[i] = p->hb[i]; }
+            std::string why;
+            if (!tc_plan_create(tm, &p->tc, &why)) {
+                errors->push_back("Failed to set up the tensor-core mask path: " + why);
+                return kRuntimeError;
+            }
+        }
+        KCHECK(cudaDeviceSynchronize());
+        return kSuccess;
+    }();
+    if (st != kSuccess) {
+        delete eng;
+        return st;
+    }
+    *out = eng;
+    return kSuccess;
+}
+
+Engine::~Engine() {
+    if (!p_) return;
+    cudaSetDevice(device_);
+    if (p_->stream) cudaStreamSynchronize(p_->stream);
+    if (p_->tc) tc_plan_destroy(p_->tc);
+    delete p_->prof;
+    for (void *a : p_->allocs) cudaFree(a);
+    if (p_->d_in) cudaFree(p_->d_in);
+    if (p_->d_out) cudaFree(p_->d_out);
+    if (p_->stream) cudaStreamDestroy(p_->stream);
+    delete p_;
+}
+
+Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long long stride, void *stream_,
+                              std::vector<std::string> *errors) {
+    if (!pcm || !out || frames < 0 || stride < kFrame || (stride & 7) || ((uintptr_t) pcm & 15) || ((uintptr_t) out & 15)) {
+        if (errors) errors->push_back("PCM buffers must be non-NULL, 16-byte aligned, with a stream stride >= 256 and a multiple of 8.");
+        return kInvalidArgument;
+    }
+    Impl *p = p_;
+    KCHECK(cudaSetDevice(device_));
+    cudaStream_t st = stream_ ? (cudaStream_t) stream_ : p->stream;
+    const int B = n_, Bp = npad_, H = p->H, L = p->L;
+    const size_t LBH = (size_t) Bp * H;
+    const int stft_grid = (B + kStftWarps - 1) / kStftWarps;
+    KernelProfiler *prof = p->prof;
+    for (int t = 0; t < frames; t++) {
+        PcmView v{pcm, out, stride, t};
+        const int cur = p->parity, nxt = cur ^ 1;
+        if (precision_ == kFp32) {
+            float *feat = (float *) p->feat, *e = (float *) p->e;
+            if (prof) prof->begin(kKernFrontend, st);
+            frontend_kernel<float><<<stft_grid, kStftWarps * 32, 0, st>>>(v, B, p->tail, p->spec, feat, p->tables);
+            if (prof) { prof->end(st); prof->begin(kKernEnc, st); }
+            linear_fp32_kernel<kActRelu><<<dim3(Bp / kF32Bm, H / 64), 256, 0, st>>>(feat, p->enc_w, p->enc_b, e, kBins, H);
+            if (prof) prof->end(st);
+            const float *x = e;
+            for (int l = 0; l < L; l++) {
+                if (prof) prof->begin(kKernGru, st);
+                gru_fp32_kernel<<<dim3(Bp / kF32Bm, H / 16), 256, 0, st>>>(x, p->h[cur] + l * LBH, p->h[nxt] + l * LBH,
+                                                                            p->wih[l], p->whh[l], p->bih[l], p->bhh[l], H);
+                if (prof) prof->end(st);
+                x = p->h[nxt] + l * LBH;
+            }
+            if (prof) prof->begin(kKernDec, st);
+            linear_fp32_kernel<kActSigmoid><<<dim3(Bp / kF32Bm, kBins / 64), 256, 0, st>>>(x, p->dec_w, p->dec_b, p->mask, H, kBins);
+            if (prof) prof->end(st);
+            launches_ += 3 + L;
+        } else {
+            if (prof) prof->begin(kKernFrontend, st);
+            frontend_kernel<__nv_bfloat16><<<stft_grid, kStftWarps * 32, 0, st>>>(v, B, p->tail, p->spec,
+                                                                                  (__nv_bfloat16 *) p->feat, p->tables);
+            if (prof) prof->end(st);
+            launches_ += 1 + tc_masknet_step(p->tc, cur, st, prof);
+        }
+        if (prof) prof->begin(kKernBackend, st);
+        backend_kernel<<<stft_grid, kStftWarps * 32, 0, st>>>(v, B, p->spec, p->mask, p->ola, p->tables);
+        if (prof) prof->end(st);
+        launches_ += 1;
+        p->parity = nxt;
+    }
+    KCHECK(cudaGetLastError());
+    return kSuccess;
+}
+
+Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::vector<std::string> *errors) {
+    if (!pcm || !out || frames < 0) {
+        if (errors) errors->push_back("PCM buffers must be non-NULL.");
+        return kInvalidArgument;
+    }
+    if (frames == 0) return kSuccess;
+    Impl *p = p_;
+    KCHECK(cudaSetDevice(device_));
+    if ((size_t) frames > p->staging_frames) {
+        if (p->d_in) cudaFree(p->d_in);
+        if (p->d_out) cudaFree(p->d_out);
+        p->d_in = p->d_out = nullptr;
+        p->staging_frames = 0;
+        KCHECK(cudaMalloc((void **) &p->d_in, (size_t) n_ * frames * kFrame * sizeof(int16_t)));
+        KCHECK(cudaMalloc((void **) &p->d_out, (size_t) n_ * frames * kFrame * sizeof(int16_t)));
+        p->staging_frames = frames;
+    }
+    const size_t bytes = (size_t) n_ * frames * kFrame * sizeof(int16_t);
+    KCHECK(cudaMemcpyAsync(p->d_in, pcm, bytes, cudaMemcpyHostToDevice, p->stream));
+    Status st = process_device(p->d_in, p->d_out, frames, (long long) frames * kFrame, nullptr, errors);
+    if (st != kSuccess) return st;
+    KCHECK(cudaMemcpyAsync(out, p->d_out, bytes, cudaMemcpyDeviceToHost, p->stream));
+    KCHECK(cudaStreamSynchronize(p->stream));
+    return kSuccess;
+}
+
+__global__ void reset_streams_kernel(const int32_t *__restrict__ ids, int n_ids, int n_streams, int16_t *tail, float *ola,
+                                     float *h0, float *h1, __nv_bfloat16 *hb0, __nv_bfloat16 *hb1, int H, int L, size_t LBH) {
+    const int i = blockIdx.x;
+    if (i >= n_ids) return;
+    const int s = ids[i];
+    if (s < 0 || s >= n_streams) return;
+    for (int k = threadIdx.x; k < kFrame; k += blockDim.x) {
+        tail[(size_t) s * kFrame + k] = 0;
+        ola[(size_t) s * kFrame + k] = 0.0f;
+    }
+    for (int l = 0; l < L; l++)
+        for (int k = threadIdx.x; k < H; k += blockDim.x) {
+            const size_t idx = l * LBH + (size_t) s * H + k;
+            h0[idx] = 0.0f;
+            h1[idx] = 0.0f;
+            if (hb0) {
+                hb0[idx] = __float2bfloat16(0.0f);
+                hb1[idx] = __float2bfloat16(0.0f);
+            }
+        }
+}
+
+Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> *errors) {
+    Impl *p = p_;
+    KCHECK(cudaSetDevice(device_));
+    const size_t Bp = npad_, H = p->H, L = p->L;
+    if (!stream_ids) {
+        KCHECK(cudaMemsetAsync(p->tail, 0, Bp * kFrame * sizeof(int16_t), p->stream));
+        KCHECK(cudaMemsetAsync(p->ola, 0, Bp * kFrame * sizeof(float), p->stream));
+        for (int i = 0; i < 2; i++) {
+            KCHECK(cudaMemsetAsync(p->h[i], 0, L * Bp * H * sizeof(float), p->stream));
+            if (p->hb[i]) KCHECK(cudaMemsetAsync(p->hb[i], 0, L * Bp * H * sizeof(__nv_bfloat16), p->stream));
+        }
+    } else {
+        if (n < 0) {
+            if (errors) errors->push_back("Negative stream count.");
+            return kInvalidArgument;
+        }
+        for (int i = 0; i < n; i++)
+            if (stream_ids[i] < 0 || stream_ids[i] >= n_) {
+                if (errors) errors->push_back("Stream id out of range.");
+                return kInvalidArgument;
+            }
+        if (n > 0) {
+            int32_t *d_ids = nullptr;
+            KCHECK(cudaMalloc((void **) &d_ids, n * sizeof(int32_t)));
+            cudaError_t e1 = cudaMemcpyAsync(d_ids, stream_ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream);
+            reset_streams_kernel<<<n, 128, 0, p->stream>>>(d_ids, n, n_, p->tail, p->ola, p->h[0], p->h[1], p->hb[0], p->hb[1],
+                                                          (int) H, (int) L, Bp * H);
+            cudaError_t e2 = cudaStreamSynchronize(p->stream);
+            cudaFree(d_ids);
+            KCHECK(e1);
+            KCHECK(e2);
+        }
+    }
+    KCHECK(cudaStreamSynchronize(p->stream));
+    return kSuccess;
+}
+
+void Engine::set_profile(bool on) {
+    if (on && !p_->prof) p_->prof = new KernelProfiler();
+    if (!on) {
+        delete p_->prof;
+        p_->prof = nullptr;
+    }
+}
+
+Status Engine::profile_read(double *ms, long long *count, int n_classes, std::vector<std::string> *errors) {
+    if (!p_->prof || n_classes < kKernClasses) {
+        if (errors) errors->push_back("Profiling is not enabled.");
+        return kInvalidState;
+    }
+    KCHECK(cudaSetDevice(device_));
+    KCHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < n_classes; i++) { ms[i] = 0.0; count[i] = 0; }
+    p_->prof->drain(ms, count);
+    return kSuccess;
+}
+
+Status Engine::synchronize(std::vector<std::string> *errors) {
+    KCHECK(cudaSetDevice(device_));
+    KCHECK(cudaStreamSynchronize(p_->stream));
+    return kSuccess;
+}
+
+Status Engine::debug_read(const char *name, void *dst, size_t bytes, std::vector<std::string> *errors) {
+    Impl *p = p_;
+    KCHECK(cudaSetDevice(device_));
+    KCHECK(cudaDeviceSynchronize());
+    const size_t B = n_, Bp = npad_, H = p->H;
+    const void *src = nullptr;
+    size_t avail = 0;
+    const size_t esz = precision_ == kFp32 ? 4 : 2;
+    const std::string nm(name ? name : "");
+    if (nm == "feat") { src = p->feat; avail = B * kBins * esz; }
+    else if (nm == "spec") { src = p->spec; avail = B * kNfft * 4; }
+    else if (nm == "mask") { src = p->mask; avail = B * kBins * 4; }
+    else if (nm == "e") { src = p->e; avail = B * H * esz; }
+    else if (nm == "ola") { src = p->ola; avail = B * kFrame * 4; }
+    else if (nm == "tail") { src = p->tail; avail = B * kFrame * 2; }
+    else if (nm.size() == 2 && nm[0] == 'h' && nm[1] >= '0' && nm[1] < '0' + p->L) {
+        src = p->h[p->parity] + (size_t) (nm[1] - '0') * Bp * H;   // h(t) of the last finished step
+        avail = B * H * 4;
+    }
+    if (!src || bytes > avail) {
+        if (errors) errors->push_back("Unknown tensor name or size too large.");
+        return kInvalidArgument;
+    }
+    KCHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return kSuccess;
+}
+
+}  // namespace koala

@@ -1,0 +1,198 @@
+// koala_b200 -- shared constants and small device helpers (sm_100a only).
+//
+// The path implemented here is the inside of `pv_koala_process` (/root/reference/include/pv_koala.h:65-80), which the
+// reference ships only as a closed binary; the signal path is SPEC.md of this repository, the contract is the header's.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace koala {
+
+constexpr int kFrame = 256;      // pv_koala_frame_length()  (pv_koala.h:102-107)
+constexpr int kSampleRate = 16000;  // pv_sample_rate()      (picovoice.h:33-36)
+constexpr int kNfft = 512;
+constexpr int kBins = 256;       // bins fed to the mask estimator; Nyquist bin reuses mask[255]
+constexpr int kDelay = 256;      // pv_koala_delay_sample()  (pv_koala.h:92-100)
+constexpr int kMaxLayers = 8;
+
+constexpr float kFeatPowerScale = 9.31322574615478515625e-10f;  // 2^-30
+constexpr float kFeatEps = 1e-6f;
+constexpr float kFeatGain = 0.125f;
+constexpr float kFeatBias = 0.25f;
+
+enum Precision : int { kFp32 = 0, kBf16 = 1 };
+
+// kernel classes of one step, in launch order (per-class timing for bench.py's roofline object)
+enum KernelClass : int { kKernFrontend = 0, kKernEnc = 1, kKernGru = 2, kKernDec = 3, kKernBackend = 4, kKernClasses = 5 };
+
+// Optional per-launch CUDA-event timing on the launching stream (off by default: events perturb back-to-back launches).
+struct KernelProfiler {
+    struct Span { int cls; cudaEvent_t a, b; };
+    Span *spans = nullptr;
+    int n = 0, cap = 0;
+    void begin(int cls, cudaStream_t st) {
+        if (n == cap) {
+            const int ncap = cap ? 2 * cap : 1024;
+            Span *ns = new Span[ncap];
+            for (int i = 0; i < n; i++) ns[i] = spans[i];
+            delete[] spans;
+            spans = ns;
+            cap = ncap;
+        }
+        spans[n].cls = cls;
+        cudaEventCreate(&spans[n].a);
+        cudaEventCreate(&spans[n].b);
+        cudaEventRecord(spans[n].a, st);
+    }
+    void end(cudaStream_t st) { cudaEventRecord(spans[n++].b, st); }
+    // sums elapsed ms per class and releases the events; the caller must have synchronised the stream
+    void drain(double *ms, long long *count) {
+        for (int i = 0; i < n; i++) {
+            float t = 0.0f;
+            if (cudaEventElapsedTime(&t, spans[i].a, spans[i].b) == cudaSuccess) {
+                ms[spans[i].cls] += t;
+                count[spans[i].cls] += 1;
+            }
+            cudaEventDestroy(spans[i].a);
+            cudaEventDestroy(spans[i].b);
+        }
+        n = 0;
+    }
+    ~KernelProfiler() {
+        double ms[kKernClasses] = {};
+        long long c[kKernClasses] = {};
+        drain(ms, c);
+        delete[] spans;
+    }
+};
+
+// Where one step's PCM lives: frame t of stream s starts at pcm + s * stride + t * 256 (samples).
+struct PcmView {
+    const int16_t *in;
+    int16_t *out;
+    long long stride;   // samples between consecutive streams
+    int t;              // frame index inside the caller's buffer
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// complex helpers
+struct cpx { float x, y; };
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cpx cmul(cpx a, cpx w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
+__device__ __forceinline__ cpx cmulc(cpx a, cpx w) { return {a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y}; }  // a * conj(w)
+__device__ __forceinline__ cpx shfl_xor_c(cpx v, int m) {
+    return {__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m)};
+}
+__device__ __forceinline__ cpx shfl_c(cpx v, int src) {
+    return {__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
+}
+__device__ __forceinline__ int rev5(int v) { return (int) (__brev((unsigned) v) >> 27); }
+
+// One warp = one 256-point complex FFT.  Lane l, register j hold element p = l + 32 j.
+// Forward: radix-2 DIF, natural order in -> bit-reversed out: after the call z[j] = Z[8 * rev5(lane) + rev3(j)].
+// tw[k] = exp(-2 pi i k / 512), k = 0..255 (float2 in shared memory).
+__device__ __forceinline__ void warp_fft256_dif(cpx (&z)[8], const float2 *tw, int lane) {
+#pragma unroll
+    for (int dj = 4; dj >= 1; dj >>= 1) {   // spans 128, 64, 32: partner is another register of the same lane
+        const int mul = 8 / dj;             // 256 / span
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j & dj) continue;
+            const float2 w2 = tw[(lane + 32 * (j % dj)) * mul];
+            const cpx a = z[j], b = z[j + dj];
+            z[j] = cadd(a, b);
+            z[j + dj] = cmul(csub(a, b), cpx{w2.x, w2.y});
+        }
+    }
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {     // spans 16..1: partner is lane ^ h
+        const float2 w2 = tw[(lane & (h - 1)) * (256 / h)];
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const cpx v = z[j], o = shfl_xor_c(v, h);
+            z[j] = up ? cmul(csub(o, v), cpx{w2.x, w2.y}) : cadd(v, o);
+        }
+    }
+}
+
+// Inverse: radix-2 DIT with conjugate twiddles, bit-reversed in (layout produced by warp_fft256_dif) -> natural out.
+// No 1/256 scaling is applied.
+__device__ __forceinline__ void warp_ifft256_dit(cpx (&z)[8], const float2 *tw, int lane) {
+#pragma unroll
+    for (int h = 1; h <= 16; h <<= 1) {
+        const float2 w2 = tw[(lane & (h - 1)) * (256 / h)];
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const cpx t = up ? cmulc(z[j], cpx{w2.x, w2.y}) : z[j];
+            const cpx o = shfl_xor_c(t, h);
+            z[j] = up ? csub(o, t) : cadd(t, o);
+        }
+    }
+#pragma unroll
+    for (int dj = 1; dj <= 4; dj <<= 1) {
+        const int mul = 8 / dj;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j & dj) continue;
+            const float2 w2 = tw[(lane + 32 * (j % dj)) * mul];
+            const cpx a = z[j], b = cmulc(z[j + dj], cpx{w2.x, w2.y});
+            z[j] = cadd(a, b);
+            z[j + dj] = csub(a, b);
+        }
+    }
+}
+
+// register index holding the partner bin 256 - k of register j (k = 8 a + rev3(j)); see DESIGN.md "FFT layout"
+__device__ __forceinline__ constexpr int partner_reg(int j) {
+    return j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 3 : j == 3 ? 2 : j == 4 ? 7 : j == 5 ? 6 : j == 6 ? 5 : 4;
+}
+__device__ __forceinline__ constexpr int rev3c(int j) { return ((j & 1) << 2) | (j & 2) | ((j >> 2) & 1); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk copy (TMA engine, no tensor map) used to stage lookup tables into shared memory
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// accurate-enough transcendental forms shared by every epilogue (abs error ~1e-7, see SPEC.md "numerics")
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) {
+    // 1 - 2 / (1 + e^{2x}); saturates cleanly for |x| large (e^{2x} -> inf => 1, -> 0 => -1)
+    return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+}
+
+}  // namespace koala

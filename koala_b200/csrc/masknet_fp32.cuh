@@ -1,0 +1,137 @@
+// koala_b200 -- mask estimator, fp32 path (BASELINE.json configs[1]: "fp32 mask path").
+//
+// Middle stage of `pv_koala_process` (/root/reference/include/pv_koala.h:65-80).  The reference's counterparts are its
+// int8 x int16 mat-vec kernels and LUT gate kernels (taabe36/159/174/225, taabe84/26/115), one
+// stream at a time; here the batch of streams is the GEMM M dimension.  Operands: activations fp32, weights bf16 in HBM
+// (exactly representable, widened on load), fp32 FMA accumulation, gates/state fp32 and fused into the GEMM epilogue.
+#pragma once
+
+#include "koala_common.cuh"
+
+namespace koala {
+
+constexpr int kF32Bm = 64;     // streams per CTA
+constexpr int kF32Bk = 16;
+constexpr int kF32Pad = 4;
+
+enum Act : int { kActRelu = 0, kActSigmoid = 1 };
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 &u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// stage a [64 rows][16 k] fp32 activation tile transposed into As[k][row]
+__device__ __forceinline__ void load_a_tile(float (*As)[kF32Bm + kF32Pad], const float *__restrict__ A, int lda, int m0,
+                                            int k0, int tid) {
+    const int row = tid >> 2, kc = (tid & 3) * 4;
+    const float4 v = *reinterpret_cast<const float4 *>(A + (size_t) (m0 + row) * lda + k0 + kc);
+    As[kc + 0][row] = v.x; As[kc + 1][row] = v.y; As[kc + 2][row] = v.z; As[kc + 3][row] = v.w;
+}
+
+// out[m][n] = act(bias[n] + sum_k A[m][k] W[n][k]);  grid = (M/64, N/64), block = 256 (tx = 16 columns x 4, ty = 16 x 4 rows)
+template <int ACT>
+__global__ void __launch_bounds__(256)
+linear_fp32_kernel(const float *__restrict__ A, const __nv_bfloat16 *__restrict__ W, const float *__restrict__ bias,
+                   float *__restrict__ out, int K, int N) {
+    __shared__ __align__(16) float As[kF32Bk][kF32Bm + kF32Pad];
+    __shared__ __align__(16) float Ws[kF32Bk][64 + kF32Pad];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * kF32Bm, n0 = blockIdx.y * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += kF32Bk) {
+        load_a_tile(As, A, K, m0, k0, tid);
+        if (tid < 128) {
+            const int row = tid >> 1, kc = (tid & 1) * 8;
+            float f[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4 *>(W + (size_t) (n0 + row) * K + k0 + kc), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Ws[kc + i][row] = f[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kF32Bk; ++kk) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            float wv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wv[c] = Ws[kk][tx + 16 * c];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int m = m0 + ty * 4 + r, n = n0 + tx + 16 * c;
+            const float v = acc[r][c] + bias[n];
+            out[(size_t) m * N + n] = ACT == kActRelu ? fmaxf(v, 0.0f) : sigmoid_f(v);
+        }
+}
+
+// One GRU layer step for a tile of 64 streams x 16 hidden units (PyTorch gate order r | z | n):
+//   r = sig(Wir x + bir + Whr h + bhr), z = sig(Wiz x + biz + Whz h + bhz), n = tanh(Win x + bin + r (Whn h + bhn)),
+//   h' = (1 - z) n + z h.
+// grid = (M/64, H/16), block = 256 (tx = unit, ty = 16 x 4 rows).  h_prev and h_next are different buffers (ping-pong):
+// other CTAs still read h_prev rows as their GEMM operand while this one writes its 16 units of h_next.
+__global__ void __launch_bounds__(256)
+gru_fp32_kernel(const float *__restrict__ x, const float *__restrict__ h_prev, float *__restrict__ h_next,
+                const __nv_bfloat16 *__restrict__ Wih, const __nv_bfloat16 *__restrict__ Whh,
+                const float *__restrict__ bih, const float *__restrict__ bhh, int H) {
+    __shared__ __align__(16) float As[kF32Bk][kF32Bm + kF32Pad];
+    __shared__ __align__(16) float Ws[kF32Bk][48 + kF32Pad];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * kF32Bm, u0 = blockIdx.y * 16;
+    float ar[4] = {}, az[4] = {}, anx[4] = {}, anh[4] = {};
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+        const float *A = part == 0 ? x : h_prev;
+        const __nv_bfloat16 *W = part == 0 ? Wih : Whh;
+        for (int k0 = 0; k0 < H; k0 += kF32Bk) {
+            load_a_tile(As, A, H, m0, k0, tid);
+            if (tid < 96) {   // 48 weight rows (3 gates x 16 units) x 16 k
+                const int row = tid >> 1, kc = (tid & 1) * 8;
+                const int g = row >> 4, u = row & 15;
+                float f[8];
+                bf16x8_to_f32(*reinterpret_cast<const uint4 *>(W + (size_t) (g * H + u0 + u) * H + k0 + kc), f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Ws[kc + i][row] = f[i];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < kF32Bk; ++kk) {
+                const float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float wr = Ws[kk][tx], wz = Ws[kk][16 + tx], wn = Ws[kk][32 + tx];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    ar[r] = fmaf(av[r], wr, ar[r]);
+                    az[r] = fmaf(av[r], wz, az[r]);
+                    if (part == 0) anx[r] = fmaf(av[r], wn, anx[r]);
+                    else anh[r] = fmaf(av[r], wn, anh[r]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int u = u0 + tx;
+    const float br = bih[u] + bhh[u], bz = bih[H + u] + bhh[H + u], bnx = bih[2 * H + u], bnh = bhh[2 * H + u];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const size_t idx = (size_t) (m0 + ty * 4 + r) * H + u;
+        const float rg = sigmoid_f(ar[r] + br);
+        const float zg = sigmoid_f(az[r] + bz);
+        const float ng = tanh_f(anx[r] + bnx + rg * (anh[r] + bnh));
+        h_next[idx] = (1.0f - zg) * ng + zg * h_prev[idx];
+    }
+}
+
+}  // namespace koala

@@ -1,0 +1,439 @@
+// koala_b200 -- mask estimator, tensor-core path (BASELINE.json configs[2..4]: "bf16 tensor-core mask-estimator GEMMs").
+//
+// Middle stage of `pv_koala_process` (/root/reference/include/pv_koala.h:65-80); replaces the reference's per-stream
+// int8 x int16 dp2a mat-vec + LUT gate kernels by batched GEMMs over the stream dimension:
+// bf16 operands staged by TMA into 128B-swizzled shared memory, tcgen05.mma (cta_group::1, M = 128) accumulating fp32
+// in TMEM, gates / state update / activation fused into the epilogue that reads TMEM back with tcgen05.ld.
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+// (one TMEM lane quarter each).  Two accumulator buffers of 256 TMEM columns let the epilogue of tile i overlap the MMAs
+// of tile i+1.
+//
+// GRU tile = 128 streams x 64 hidden units.  TMEM columns: [r 0..63 | z 64..127 | n_x 128..191 | n_h 192..255].
+//   x-part (K = H):  one N=192 MMA per k-step   (packed W_ih rows r|z|n of the 64 units)        -> cols 0..191
+//   h-part (K = H):  N=128 MMA (W_hh rows r|z) accumulating on cols 0..127, N=64 MMA (W_hh rows n) -> cols 192..255
+// Linear tile = 128 streams x 256 outputs, one N=256 MMA per k-step.
+#pragma once
+
+#include <cuda.h>
+
+#include <string>
+
+#include "koala_common.cuh"
+
+namespace koala {
+
+constexpr int kTcBlockM = 128;
+constexpr int kTcBlockK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kTcStages = 4;
+constexpr int kTcABytes = kTcBlockM * 128;    // 16 KB
+constexpr int kTcBBytesMax = 256 * 128;       // 32 KB
+constexpr int kTcStageBytes = kTcABytes + kTcBBytesMax;
+constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kTcThreads = 192;
+constexpr int kTcAccCols = 256;
+constexpr int kGruUnits = 64;                 // hidden units per GRU tile
+constexpr int kGruRows = 3 * kGruUnits;       // packed weight rows per tile
+
+enum TcMode : int { kTcEnc = 0, kTcGru = 1, kTcDec = 2 };
+
+struct TcArgs {
+    int num_m_tiles, num_n_tiles;
+    int kb_per_part;            // K / 64 of one operand part (GRU has two parts: x then h)
+    int H;
+    const float *bias0;         // enc/dec bias | GRU b_ih
+    const float *bias1;         // GRU b_hh
+    const float *h_prev;        // GRU fp32 state in  [Bp][H]
+    float *h_next;              // GRU fp32 state out [Bp][H]
+    __nv_bfloat16 *out_bf16;    // enc: e [Bp][H]; GRU: bf16 copy of h_next
+    float *out_f32;             // dec: mask [Bp][256]
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows at 128 B pitch, 8-row groups at 1024 B (SBO), version 1 (sm_100), layout 2
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    return (uint64_t) ((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t) 1 << 16) | ((uint64_t) (1024 >> 4) << 32) |
+           ((uint64_t) 1 << 46) | ((uint64_t) 2 << 61);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint4 pack_bf16x8(const float *f) {
+    uint4 u;
+    __nv_bfloat162 p;
+    p = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&p);
+    p = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&p);
+    p = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&p);
+    p = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&p);
+    return u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                  const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1, const TcArgs args) {
+    constexpr bool kGru = MODE == kTcGru;
+    constexpr int kBRows = kGru ? kGruRows : 256;
+    constexpr uint32_t kStageTx = kTcABytes + kBRows * 128;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTcStages * kTcStageBytes);
+    uint64_t *full_bar = bars, *empty_bar = bars + kTcStages;
+    uint64_t *tmem_full = bars + 2 * kTcStages, *tmem_empty = bars + 2 * kTcStages + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTcStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a0);
+        prefetch_tmap(&map_b0);
+        if (kGru) {
+            prefetch_tmap(&map_a1);
+            prefetch_tmap(&map_b1);
+        }
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * kTcAccCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+    const int num_kb = (kGru ? 2 : 1) * args.kb_per_part;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m = tile / args.num_n_tiles, n = tile % args.num_n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], kStageTx);
+                    uint8_t *sa = smem + stage * kTcStageBytes, *sb = sa + kTcABytes;
+                    const bool second = kGru && kb >= args.kb_per_part;
+                    const int kc = (second ? kb - args.kb_per_part : kb) * kTcBlockK;
+                    tma_load_2d(second ? &map_a1 : &map_a0, &full_bar[stage], sa, kc, m * kTcBlockM);
+                    tma_load_2d(second ? &map_b1 : &map_b0, &full_bar[stage], sb, kc, n * kBRows);
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            int stage = 0, phase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[ab], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + ab * kTcAccCols;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kTcStageBytes), sb = sa + kTcABytes;
+                    const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < kTcBlockK / 16; ++k) {
+                        const uint64_t ad = adesc + 2 * k, bd = bdesc + 2 * k;   // +32 B per 16-element k-step
+                        if (!kGru) {
+                            umma_bf16(d, ad, bd, make_idesc(128, 256), (kb | k) != 0);
+                        } else if (kb < args.kb_per_part) {
+                            umma_bf16(d, ad, bd, make_idesc(128, 192), (kb | k) != 0);
+                        } else {
+                            umma_bf16(d, ad, bd, make_idesc(128, 128), 1u);
+                            umma_bf16(d + 192, ad, bd + ((128 * 128) >> 4), make_idesc(128, 64),
+                                      (kb != args.kb_per_part || k != 0));
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[ab]);
+            }
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5 -> TMEM lane quarter warp % 4)
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m = tile / args.num_n_tiles, n = tile % args.num_n_tiles;
+            const int ab = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[ab], aphase);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t) (quarter * 32) << 16) + ab * kTcAccCols;
+            const size_t row = (size_t) m * kTcBlockM + quarter * 32 + lane;
+            if (kGru) {
+                const int H = args.H;
+#pragma unroll 1
+                for (int c = 0; c < kGruUnits / 16; ++c) {
+                    float ar[16], az[16], anx[16], anh[16];
+                    tmem_ld16(t0 + 0 + c * 16, ar);
+                    tmem_ld16(t0 + 64 + c * 16, az);
+                    tmem_ld16(t0 + 128 + c * 16, anx);
+                    tmem_ld16(t0 + 192 + c * 16, anh);
+                    const int u0 = n * kGruUnits + c * 16;
+                    float hp[16], hn[16];
+                    const float4 *hp4 = reinterpret_cast<const float4 *>(args.h_prev + row * H + u0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 t = hp4[q];
+                        hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int u = u0 + i;
+                        const float br = __ldg(args.bias0 + u) + __ldg(args.bias1 + u);
+                        const float bz = __ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u);
+                        const float rg = sigmoid_f(ar[i] + br);
+                        const float zg = sigmoid_f(az[i] + bz);
+                        const float ng = tanh_f(anx[i] + __ldg(args.bias0 + 2 * H + u) + rg * (anh[i] + __ldg(args.bias1 + 2 * H + u)));
+                        hn[i] = (1.0f - zg) * ng + zg * hp[i];
+                    }
+                    float4 *ho4 = reinterpret_cast<float4 *>(args.h_next + row * H + u0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ho4[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+                    uint4 *hb4 = reinterpret_cast<uint4 *>(args.out_bf16 + row * H + u0);
+                    hb4[0] = pack_bf16x8(hn);
+                    hb4[1] = pack_bf16x8(hn + 8);
+                }
+            } else {
+                const int N = args.num_n_tiles * 256;
+#pragma unroll 1
+                for (int c = 0; c < 256 / 16; ++c) {
+                    float acc[16];
+                    tmem_ld16(t0 + c * 16, acc);
+                    tmem_ld_wait();
+                    const int n0 = n * 256 + c * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float v = acc[i] + __ldg(args.bias0 + n0 + i);
+                        acc[i] = MODE == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
+                    }
+                    if (MODE == kTcEnc) {
+                        uint4 *o = reinterpret_cast<uint4 *>(args.out_bf16 + row * N + n0);
+                        o[0] = pack_bf16x8(acc);
+                        o[1] = pack_bf16x8(acc + 8);
+                    } else {
+                        float4 *o = reinterpret_cast<float4 *>(args.out_f32 + row * N + n0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[ab]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * kTcAccCols);
+    }
+}
+
+// packed[(n * 3 + g) * 64 + u][k] = W[g * H + n * 64 + u][k]: the three gate rows of one unit tile become contiguous
+__global__ void pack_gru_weights_kernel(const __nv_bfloat16 *__restrict__ W, __nv_bfloat16 *__restrict__ packed, int H) {
+    const int prow = blockIdx.x;
+    const int n = prow / kGruRows, g = (prow % kGruRows) / kGruUnits, u = prow % kGruUnits;
+    const uint4 *src = reinterpret_cast<const uint4 *>(W + (size_t) (g * H + n * kGruUnits + u) * H);
+    uint4 *dst = reinterpret_cast<uint4 *>(packed + (size_t) prow * H);
+    for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+struct TcModel {
+    int H = 0, L = 0, Bp = 0;
+    const __nv_bfloat16 *enc_w = nullptr, *dec_w = nullptr, *wih[kMaxLayers] = {}, *whh[kMaxLayers] = {};
+    const float *enc_b = nullptr, *dec_b = nullptr, *bih[kMaxLayers] = {}, *bhh[kMaxLayers] = {};
+    __nv_bfloat16 *feat = nullptr, *e = nullptr, *hb[2] = {};
+    float *h[2] = {}, *mask = nullptr;
+};
+
+struct TcPlan {
+    TcModel m;
+    int num_sms = 0;
+    __nv_bfloat16 *wih_p[kMaxLayers] = {}, *whh_p[kMaxLayers] = {};
+    CUtensorMap a_feat, a_e, a_hb[2][kMaxLayers];      // activation operands [Bp][K], box 64 x 128
+    CUtensorMap b_enc, b_dec, b_ih[kMaxLayers], b_hh[kMaxLayers];
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool encode_2d(EncodeTiledFn fn, CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t) kTcBlockK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static void tc_plan_destroy(TcPlan *p) {
+    if (!p) return;
+    for (int l = 0; l < kMaxLayers; l++) {
+        if (p->wih_p[l]) cudaFree(p->wih_p[l]);
+        if (p->whh_p[l]) cudaFree(p->whh_p[l]);
+    }
+    delete p;
+}
+
+static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
+    if (m.H % 256 != 0 || m.Bp % kTcBlockM != 0) {
+        *why = "hidden size must be a multiple of 256 for the tensor-core path";
+        return false;
+    }
+    void *fnp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres) != cudaSuccess || !fnp ||
+        qres != cudaDriverEntryPointSuccess) {
+        *why = "cuTensorMapEncodeTiled not available from the driver";
+        return false;
+    }
+    EncodeTiledFn fn = (EncodeTiledFn) fnp;
+    TcPlan *p = new TcPlan();
+    p->m = m;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t H = m.H, Bp = m.Bp;
+    bool ok = true;
+    for (int l = 0; l < m.L && ok; l++) {
+        ok = cudaMalloc((void **) &p->wih_p[l], 3 * H * H * 2) == cudaSuccess &&
+             cudaMalloc((void **) &p->whh_p[l], 3 * H * H * 2) == cudaSuccess;
+        if (!ok) break;
+        pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.wih[l], p->wih_p[l], (int) H);
+        pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.whh[l], p->whh_p[l], (int) H);
+    }
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+    if (!ok) {
+        *why = "packing the GRU weights failed";
+        tc_plan_destroy(p);
+        return false;
+    }
+    ok = ok && encode_2d(fn, &p->a_feat, m.feat, Bp, kBins, kTcBlockM);
+    ok = ok && encode_2d(fn, &p->a_e, m.e, Bp, H, kTcBlockM);
+    for (int par = 0; par < 2; par++)
+        for (int l = 0; l < m.L; l++) ok = ok && encode_2d(fn, &p->a_hb[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, kTcBlockM);
+    ok = ok && encode_2d(fn, &p->b_enc, m.enc_w, H, kBins, 256);
+    ok = ok && encode_2d(fn, &p->b_dec, m.dec_w, kBins, H, 256);
+    for (int l = 0; l < m.L; l++) {
+        ok = ok && encode_2d(fn, &p->b_ih[l], p->wih_p[l], 3 * H, H, kGruRows);
+        ok = ok && encode_2d(fn, &p->b_hh[l], p->whh_p[l], 3 * H, H, kGruRows);
+    }
+    if (!ok) {
+        *why = "cuTensorMapEncodeTiled failed";
+        tc_plan_destroy(p);
+        return false;
+    }
+    ok = cudaFuncSetAttribute(tc_masknet_kernel<kTcEnc>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(tc_masknet_kernel<kTcGru>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(tc_masknet_kernel<kTcDec>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
+    if (!ok) {
+        *why = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+        tc_plan_destroy(p);
+        return false;
+    }
+    *out = p;
+    return true;
+}
+
+// one mask-estimator step: hb[cur]/h[cur] hold state t-1, results go to hb[cur^1]/h[cur^1]; returns kernels launched
+static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *prof) {
+    const TcModel &m = p->m;
+    const int nxt = cur ^ 1, H = m.H, mt = m.Bp / kTcBlockM;
+    const size_t LBH = (size_t) m.Bp * H;
+    auto grid = [&](int tiles) { return tiles < p->num_sms ? tiles : p->num_sms; };
+    {
+        TcArgs a{};
+        a.num_m_tiles = mt; a.num_n_tiles = H / 256; a.kb_per_part = kBins / kTcBlockK; a.H = H;
+        a.bias0 = m.enc_b; a.out_bf16 = m.e;
+        if (prof) prof->begin(kKernEnc, st);
+        tc_masknet_kernel<kTcEnc><<<grid(mt * a.num_n_tiles), kTcThreads, kTcSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, a);
+        if (prof) prof->end(st);
+    }
+    for (int l = 0; l < m.L; l++) {
+        TcArgs a{};
+        a.num_m_tiles = mt; a.num_n_tiles = H / kGruUnits; a.kb_per_part = H / kTcBlockK; a.H = H;
+        a.bias0 = m.bih[l]; a.bias1 = m.bhh[l];
+        a.h_prev = m.h[cur] + l * LBH; a.h_next = m.h[nxt] + l * LBH; a.out_bf16 = m.hb[nxt] + l * LBH;
+        const CUtensorMap &ax = l == 0 ? p->a_e : p->a_hb[nxt][l - 1];
+        if (prof) prof->begin(kKernGru, st);
+        tc_masknet_kernel<kTcGru><<<grid(mt * a.num_n_tiles), kTcThreads, kTcSmemBytes, st>>>(ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], a);
+        if (prof) prof->end(st);
+    }
+    {
+        TcArgs a{};
+        a.num_m_tiles = mt; a.num_n_tiles = kBins / 256; a.kb_per_part = H / kTcBlockK; a.H = H;
+        a.bias0 = m.dec_b; a.out_f32 = m.mask;
+        if (prof) prof->begin(kKernDec, st);
+        tc_masknet_kernel<kTcDec><<<grid(mt * a.num_n_tiles), kTcThreads, kTcSmemBytes, st>>>(p->a_hb[nxt][m.L - 1], p->a_hb[nxt][m.L - 1], p->b_dec, p->b_dec, a);
+        if (prof) prof->end(st);
+    }
+    return 2 + m.L;
+}
+
+}  // namespace koala

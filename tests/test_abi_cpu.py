@@ -1,0 +1,137 @@
+"""CPU-side checks of the C-ABI boundary: the library loads without a GPU, exports every declared symbol, and answers the
+key-less calls exactly as the reference binary does (tests/golden/abi_kat.json, recorded by tools/make_abi_kat.py)."""
+import json
+import os
+import re
+import threading
+from ctypes import CDLL, POINTER, byref, c_char_p, c_int32, c_short, c_void_p
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+@pytest.fixture(scope="module")
+def kat():
+    with open(os.path.join(GOLDEN, "abi_kat.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def lib(library_path):
+    lib = CDLL(library_path)
+    lib.pv_koala_version.restype = c_char_p
+    lib.pv_status_to_string.restype = c_char_p
+    lib.pv_get_sdk.restype = c_char_p
+    return lib
+
+
+def _stack(lib):
+    ms, d = POINTER(c_char_p)(), c_int32(-7)
+    st = lib.pv_get_error_stack(byref(ms), byref(d))
+    out = [ms[i].decode() for i in range(d.value)] if d.value > 0 else []
+    lib.pv_free_error_stack(ms)
+    return st, d.value, [m.split(": ", 1)[1] for m in out], out
+
+
+def test_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "pv_koala_b200.h")).read()
+    declared = set(re.findall(r"PV_API[^;(]*?\b(pv_\w+)\s*\(", header))
+    assert len(declared) >= 28
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_exports_cover_the_reference_binary(lib, kat):
+    for name in kat["exports"]:          # the 18 pv_* symbols `nm -D` shows on the reference .so
+        assert hasattr(lib, name), name
+
+
+def test_constants_match_reference(lib, kat):
+    assert lib.pv_koala_frame_length() == kat["frame_length"] == 256
+    assert lib.pv_sample_rate() == kat["sample_rate"] == 16000
+    assert lib.pv_get_sdk().decode() == kat["default_sdk"]
+    assert len(lib.pv_koala_version()) > 0
+    for code, text in kat["status_strings"].items():
+        got = lib.pv_status_to_string(int(code))
+        assert (got.decode() if got else None) == text
+
+
+def test_error_stack_semantics_match_reference(lib, kat, tmp_path):
+    assert _stack(lib)[:2] == (kat["empty_stack"]["status"], kat["empty_stack"]["depth"])   # INVALID_STATE, 0
+    h = c_void_p()
+    model = str(tmp_path / "m.kpv").encode()
+    for name, args in {
+        "null_access_key": (None, model, b"gpu", byref(h)),
+        "null_model_path": (b"k", None, b"gpu", byref(h)),
+        "null_object": (b"k", model, b"gpu", None),
+        "bad_device_tpu": (b"invalid", model, b"tpu", byref(h)),
+        "bad_device_upper": (b"invalid", model, b"CPU", byref(h)),
+    }.items():
+        ref = kat["init"][name]
+        assert lib.pv_koala_init(*args) == ref["status"], name
+        st, depth, texts, raw = _stack(lib)
+        assert st == 0 and texts[0] == ref["stack"]["texts"][0], name
+        assert re.match(r"^\S+ [0-9A-F]{8}: ", raw[0])                   # "<tag> <8-hex code>: <text>"
+    # two failures without draining -> only the latest; a second read finds nothing pending
+    lib.pv_koala_init(b"invalid", model, b"tpu", byref(h))
+    lib.pv_koala_init(None, model, b"gpu", byref(h))
+    assert _stack(lib)[2] == kat["two_failures_keep_latest"]["stack"]["texts"]
+    assert _stack(lib)[:2] == (6, 0)
+    # device NULL: the reference segfaults, we return INVALID_ARGUMENT
+    assert lib.pv_koala_init(b"k", model, None, byref(h)) == 3
+    assert _stack(lib)[2] == ["Argument `device` is NULL."]
+
+
+def test_null_handle_behaviour_matches_reference(lib, kat):
+    buf = (c_short * 256)()
+    assert lib.pv_koala_process(None, buf, buf) == kat["process_null"]["status"]
+    st, depth, texts, _ = _stack(lib)
+    assert texts == kat["process_null"]["stack"]["texts"] and 0 < depth < 8
+    assert lib.pv_koala_reset(None) == kat["reset_null"]["status"]
+    assert _stack(lib)[:2] == (kat["reset_null"]["stack"]["status"], 0)      # reset(NULL) pushes no message
+    d = c_int32(-5)
+    assert lib.pv_koala_delay_sample(None, byref(d)) == kat["delay_null"]["status"]
+    assert d.value == kat["delay_null"]["value_after"] == -5                 # output untouched
+    assert _stack(lib)[2] == kat["delay_null"]["stack"]["texts"]
+    lib.pv_koala_delete(None)                                                # no-op
+    lib.pv_koala_batch_delete(None)
+    n = c_int32()
+    assert lib.pv_koala_list_hardware_devices(None, byref(n)) == kat["list_null_devices"]["status"]
+    assert _stack(lib)[2][-1] == kat["list_null_devices"]["last_text"]
+    devs = POINTER(c_char_p)()
+    assert lib.pv_koala_list_hardware_devices(byref(devs), None) == kat["list_null_count"]["status"]
+    assert _stack(lib)[2][-1] == kat["list_null_count"]["last_text"]
+
+
+def test_error_stack_is_thread_local(lib):
+    """a failure on one thread is invisible from another."""
+    buf = (c_short * 256)()
+    lib.pv_koala_process(None, buf, buf)
+    seen = {}
+    t = threading.Thread(target=lambda: seen.update(other=_stack(lib)[:2]))
+    t.start()
+    t.join()
+    assert seen["other"] == (6, 0)
+    assert _stack(lib)[1] == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback(lib, random_model_path):
+    """Without a reachable B200 every constructor fails with RUNTIME_ERROR; `cpu` devices are refused outright."""
+    import torch
+    h = c_void_p()
+    key = b"a29hbGFfYjIwMF9uby1saWNlbmNlLXNlcnZlcg=="
+    assert lib.pv_koala_init(key, random_model_path.encode(), b"cpu", byref(h)) == 7
+    assert "GPU-only" in _stack(lib)[2][0]
+    assert lib.pv_koala_init(key, random_model_path.encode(), b"cpu:4", byref(h)) == 7
+    _stack(lib)
+    if not torch.cuda.is_available():
+        assert lib.pv_koala_init(key, random_model_path.encode(), b"gpu", byref(h)) == 7
+        assert _stack(lib)[2][0] == "Failed to communicate with device."       # same text as the reference's gpu:3 probe
+        b = c_void_p()
+        assert lib.pv_koala_batch_init(random_model_path.encode(), b"best", 8, b"bf16", byref(b)) == 7
+        _stack(lib)
+    b = c_void_p()
+    assert lib.pv_koala_batch_init(random_model_path.encode(), b"best", 0, b"bf16", byref(b)) == 3
+    assert lib.pv_koala_batch_init(random_model_path.encode(), b"best", 8, b"int8", byref(b)) == 3
+    _stack(lib)

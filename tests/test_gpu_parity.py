@@ -1,0 +1,213 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (run on a B200: pytest -m gpu).
+
+Tolerances (BASELINE.json north_star): enhanced int16 within +-1 LSB of the oracle on identical frames; internal mask path
+within 1e-3 relative.  Stage tensors (features, spectrum, recurrent state) are compared with tolerances stated inline."""
+import math
+
+import numpy as np
+import pytest
+
+import koala_b200 as kb
+from oracle import Oracle, OracleBatch, OracleModel
+
+from conftest import synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+LSB_TOL = 1          # int16 output
+MASK_RTOL = 1e-3     # internal floating-point mask path
+
+
+def bf16_to_f32(a):
+    return (a.astype(np.uint32) << 16).view(np.float32)
+
+
+def run_oracle(model_path, mode, pcm):
+    ob = OracleBatch(OracleModel(model_path), pcm.shape[0], mode)
+    return ob, ob.process(pcm, threads=8)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("n_streams", [1, 37, 130])
+def test_batch_parity_against_oracle(library_path, random_model_path, precision, n_streams):
+    frames = 24
+    pcm = synth_pcm(n_streams, frames, seed=100 + n_streams)
+    eng = kb.BatchKoala(n_streams, model_path=random_model_path, precision=precision)
+    out = eng.process(pcm)
+    ob, ref = run_oracle(random_model_path, precision, pcm)
+    diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= LSB_TOL, (diff.max(), np.argwhere(diff > LSB_TOL)[:5])
+    # internal tensors of the last step
+    mask = eng.debug_read("mask", (n_streams, 256), np.float32)
+    ref_mask = np.stack([ob.stream(s).last_mask for s in range(n_streams)])
+    np.testing.assert_allclose(mask, ref_mask, rtol=MASK_RTOL, atol=1e-6)
+    for l in range(2):
+        h = eng.debug_read(f"h{l}", (n_streams, 512), np.float32)
+        ref_h = np.stack([ob.stream(s).h[l] for s in range(n_streams)])
+        np.testing.assert_allclose(h, ref_h, atol=2e-4)
+    ola = eng.debug_read("ola", (n_streams, 256), np.float32)
+    np.testing.assert_allclose(ola, np.stack([ob.stream(s).ola for s in range(n_streams)]), atol=0.25, rtol=1e-3)
+    tail = eng.debug_read("tail", (n_streams, 256), np.int16)
+    assert (tail == pcm[:, -1, :]).all()
+    eng.delete()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_frontend_stage_parity(library_path, random_model_path, precision):
+    """STFT + features of one step: spectrum within 1e-5 of its scale, features within 1e-4 (fp32) / one bf16 ulp."""
+    n = 9
+    pcm = synth_pcm(n, 2, seed=5)
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision=precision)
+    eng.process(pcm)
+    om = OracleModel(random_model_path)
+    spec = eng.debug_read("spec", (n, 512), np.float32)
+    feat = eng.debug_read("feat", (n, 256), np.float32 if precision == "fp32" else np.uint16)
+    for s in range(n):
+        o = Oracle(om, precision)
+        o.frontend(pcm[s, 0])
+        rspec, rfeat = o.frontend(pcm[s, 1])
+        np.testing.assert_allclose(spec[s], rspec, atol=1e-5 * np.abs(rspec).max())
+        if precision == "fp32":
+            np.testing.assert_allclose(feat[s], rfeat, atol=1e-4)
+        else:
+            np.testing.assert_allclose(bf16_to_f32(feat[s]), rfeat, atol=2 ** -7)   # |feat| < 2 -> bf16 ulp <= 2^-7
+    eng.delete()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_state_carry_reset_and_subset_reset(library_path, random_model_path, precision):
+    """T frames in one call == T calls of one frame (config 5 state-carry); reset == fresh (pv_koala.h:82-90)."""
+    n, frames = 6, 10
+    pcm = synth_pcm(n, frames, seed=77)
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision=precision)
+    whole = eng.process(pcm).copy()
+    eng.reset()
+    stepped = np.stack([eng.process(np.ascontiguousarray(pcm[:, t, :])) for t in range(frames)], axis=1)
+    assert (stepped == whole).all()
+    eng.reset()
+    again = eng.process(pcm)
+    assert (again == whole).all()                                   # bit-exact after reset (test_koala.py:116-129)
+    # subset reset: streams 1 and 4 restart, the others keep their state
+    eng.reset([1, 4])
+    cont = eng.process(pcm)
+    assert (cont[[1, 4]] == whole[[1, 4]]).all()
+    assert not (cont[[0, 2, 3, 5]] == whole[[0, 2, 3, 5]]).all()
+    with pytest.raises(kb.KoalaInvalidArgumentError):
+        eng.reset([6])
+    eng.delete()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_edge_inputs(library_path, random_model_path, precision):
+    n = 4
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision=precision)
+    zeros = np.zeros((n, 3, 256), np.int16)
+    assert (eng.process(zeros) == 0).all()                          # silence in -> silence out
+    full = np.empty((n, 6, 256), np.int16)
+    full[0] = 32767
+    full[1] = -32768
+    full[2] = np.where(np.arange(256) % 2 == 0, 32767, -32768)
+    full[3] = np.where(np.arange(256) % 64 < 32, 32767, -32768)
+    eng.reset()
+    out = eng.process(full)
+    _, ref = run_oracle(random_model_path, precision, full)
+    assert np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= LSB_TOL   # saturating cases
+    assert eng.process(np.zeros((n, 0, 256), np.int16)).shape == (n, 0, 256)      # empty call is a no-op
+    with pytest.raises(kb.KoalaInvalidArgumentError):
+        eng.process(np.zeros((n + 1, 1, 256), np.int16))
+    with pytest.raises(kb.KoalaInvalidArgumentError):
+        eng.process(np.zeros((n, 1, 255), np.int16))
+    eng.delete()
+
+
+def test_device_tensors_and_full_size_properties(library_path, random_model_path):
+    """BASELINE config sizes (8192 streams / GPU, bf16): properties that do not need the oracle at full size --
+    duplicated streams agree bit for bit, silent streams stay silent -- plus an oracle spot check of 24 streams."""
+    import torch
+    n, frames = 8192, 6
+    base = synth_pcm(64, frames, seed=9)
+    pcm = np.tile(base, (n // 64, 1, 1))
+    pcm[5::64] = 0
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    d_in = torch.from_numpy(pcm).cuda()
+    d_out = eng.process(d_in)
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    assert (out.reshape(n // 64, 64, frames, 256) == out[:64][None]).all()        # replicas are bit-identical
+    assert (out[5::64] == 0).all()
+    pick = [0, 1, 2, 3, 6, 7, 17, 63]
+    _, ref = run_oracle(random_model_path, "bf16", np.ascontiguousarray(pcm[pick]))
+    assert np.abs(out[pick].astype(np.int32) - ref.astype(np.int32)).max() <= LSB_TOL
+    host = eng.process(pcm) if False else None                                    # host path covered elsewhere
+    assert eng.kernel_launches == frames * 6
+    eng.delete()
+
+
+def _rms(x):
+    return math.sqrt(float(np.mean((np.asarray(x, np.float64) / 32768.0) ** 2)))
+
+
+@pytest.mark.parametrize("case", ["speech", "noise", "mixed"])
+def test_reference_behaviour_through_single_stream_abi(library_path, shipped_model_path, test_pcm, noise_pcm, case):
+    """/root/reference/binding/python/test_koala.py:71-114 restated against `Koala` (pv_koala_init/process/delete)."""
+    if case == "speech":
+        inp, ref = test_pcm, test_pcm
+    elif case == "noise":
+        inp, ref = noise_pcm, None
+    else:
+        inp = np.clip(test_pcm.astype(np.int32) + noise_pcm.astype(np.int32), -32768, 32767).astype(np.int16)
+        ref = test_pcm
+    o = kb.create(kb.ANY_ACCESS_KEY, model_path=shipped_model_path, device="gpu")
+    oracle = Oracle(OracleModel(shipped_model_path), "bf16")
+    try:
+        assert o.frame_length == 256 and o.sample_rate == 16000 and o.delay_sample == 256 and len(o.version) > 0
+        fl, delay = o.frame_length, o.delay_sample
+        for start in range(0, len(inp) - fl + 1, fl):
+            frame = o.process(inp[start:start + fl].tolist())
+            assert len(frame) == fl
+            want = oracle.process(inp[start:start + fl])
+            assert np.abs(np.asarray(frame, np.int32) - want.astype(np.int32)).max() <= LSB_TOL
+            energy = _rms(frame)
+            if ref is None or start < delay:
+                dev = energy
+            else:
+                dev = abs(energy - _rms(ref[start - delay:start - delay + fl]))
+            assert dev < 0.02
+    finally:
+        o.delete()
+
+
+def test_single_stream_reset_and_errors(library_path, shipped_model_path, test_pcm):
+    o = kb.create(kb.ANY_ACCESS_KEY, model_path=shipped_model_path)
+    frames = [test_pcm[i * 256:(i + 1) * 256].tolist() for i in range(40)]
+    o.reset()
+    first = [o.process(f) for f in frames]
+    o.reset()
+    assert all(o.process(f) == a for f, a in zip(frames, first))            # test_koala.py:116-129
+    with pytest.raises(kb.KoalaInvalidArgumentError):
+        o.process([0] * 255)
+    handle, o._handle = o._handle, None                                      # test_koala.py:164-185
+    with pytest.raises(kb.KoalaError) as e:
+        o.process([0] * 256)
+    assert 0 < len(e.value.message_stack) < 8
+    o._handle = handle
+    o.delete()
+    assert len(kb.available_devices()) > 0                                   # test_koala.py:187-192
+    assert all(d.startswith("gpu:") for d in kb.available_devices())
+
+
+def test_init_errors_on_gpu_box_match_reference_kat(library_path, shipped_model_path):
+    import json
+    import os
+    from conftest import GOLDEN
+    kat = json.load(open(os.path.join(GOLDEN, "abi_kat.json")))
+    with pytest.raises(kb.KoalaError) as e:                                  # test_koala.py:136-162
+        kb.create("invalid", model_path=shipped_model_path, device="gpu")
+    texts = [m.split(": ", 1)[1] for m in e.value.message_stack]
+    assert kat["init"]["invalid_key"]["stack"]["texts"][1] in texts          # "Failed to parse AccessKey `invalid`."
+    assert isinstance(e.value, kb.KoalaInvalidArgumentError)
+    with pytest.raises(kb.KoalaError) as e2:
+        kb.create("invalid", model_path=shipped_model_path, device="gpu")
+    assert list(e2.value.message_stack) == list(e.value.message_stack)      # repeatable
+    with pytest.raises(kb.KoalaRuntimeError):
+        kb.create(kb.ANY_ACCESS_KEY, model_path=shipped_model_path, device="gpu:99")

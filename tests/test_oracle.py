@@ -1,0 +1,139 @@
+"""CPU tests of the oracle itself: C restatement vs numpy restatement, contract properties, and the reference's own
+behavioural tests (/root/reference/binding/python/test_koala.py:71-129) run against the oracle with the shipped weights."""
+import math
+
+import numpy as np
+import pytest
+
+from koala_b200 import spec
+from oracle import Oracle, OracleBatch, OracleModel
+from oracle.numpy_oracle import NumpyOracle
+
+from conftest import synth_pcm
+
+
+@pytest.fixture(scope="module")
+def rand_models(random_model_path):
+    return OracleModel(random_model_path), spec.load_model(random_model_path)
+
+
+@pytest.fixture(scope="module")
+def shipped(shipped_model_path):
+    return OracleModel(shipped_model_path)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_c_oracle_matches_numpy_restatement(rand_models, mode):
+    om, nm = rand_models
+    o, n = Oracle(om, mode), NumpyOracle(nm, mode)
+    pcm = synth_pcm(1, 12, seed=7)[0]
+    for t in range(12):
+        a, b = o.process(pcm[t]), n.process(pcm[t])
+        assert np.abs(a.astype(int) - b.astype(int)).max() <= 1          # int16 out within 1 LSB
+        np.testing.assert_allclose(o.h, n.h, atol=2e-6)                  # recurrent state
+    np.testing.assert_allclose(o.ola, n.ola, atol=2e-2, rtol=1e-5)
+
+
+def test_stage_functions_match_numpy(rand_models):
+    om, nm = rand_models
+    o, n = Oracle(om, "fp32"), NumpyOracle(nm, "fp32")
+    pcm = synth_pcm(1, 3, seed=3)[0]
+    for t in range(3):
+        sp, feat = o.frontend(pcm[t])
+        X, nfeat = n.frontend(pcm[t])
+        scale = np.abs(X).max()
+        assert abs(sp[1] - X[256].real) <= 1e-5 * scale                  # Nyquist packed into Im slot of bin 0
+        np.testing.assert_allclose(sp[0::2][1:], X.real[1:256], atol=1e-5 * scale)
+        np.testing.assert_allclose(sp[1::2][1:], X.imag[1:256], atol=1e-5 * scale)
+        np.testing.assert_allclose(feat, nfeat, atol=1e-4)
+        mask = o.masknet(feat)
+        np.testing.assert_allclose(mask, n.masknet(nfeat), atol=1e-5)
+        assert ((mask > 0) & (mask < 1)).all()
+
+
+def test_identity_mask_is_pure_delay(rand_models):
+    """sqrt-Hann analysis x synthesis at hop 256 reconstructs exactly: mask == 1 -> output == input delayed by 256."""
+    om, _ = rand_models
+    o = Oracle(om, "fp32")
+    x = synth_pcm(1, 6, seed=11)[0] * 8
+    outs = [o.backend(o.frontend(x[t])[0], np.ones(256, np.float32)) for t in range(6)]
+    assert (outs[0] == 0).all()
+    for t in range(5):
+        assert (outs[t + 1] == x[t]).all()
+    assert Oracle.delay_sample == 256 and spec.DELAY_SAMPLE == 256
+
+
+def test_saturation_and_zero_input(rand_models):
+    om, _ = rand_models
+    o = Oracle(om, "fp32")
+    for t in range(4):
+        assert (o.process(np.zeros(256, np.int16)) == 0).all()           # zero in -> zero out, state stays zero
+    assert not o.ola.any()
+    sq = np.where(np.arange(256) % 64 < 32, 32767, -32768).astype(np.int16)
+    outs = [o.backend(o.frontend(sq)[0], np.ones(256, np.float32)) for _ in range(3)]
+    assert (outs[2] == sq).all()                                          # full-scale survives round + saturate
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_reset_is_bit_exact(rand_models, mode):
+    """test_koala.py:116-129: two passes separated by reset() are bit-identical."""
+    om, _ = rand_models
+    o = Oracle(om, mode)
+    pcm = synth_pcm(1, 10, seed=5)[0]
+    first = [o.process(f) for f in pcm]
+    o.reset()
+    second = [o.process(f) for f in pcm]
+    assert all((a == b).all() for a, b in zip(first, second))
+    fresh = Oracle(om, mode)
+    assert all((fresh.process(f) == a).all() for f, a in zip(pcm, first))
+
+
+def test_batch_equals_independent_streams(rand_models):
+    om, _ = rand_models
+    pcm = synth_pcm(19, 4, seed=9)                                        # ragged: not a multiple of the 8-stream block
+    out = OracleBatch(om, 19, "bf16").process(pcm, threads=3)
+    for s in (0, 7, 8, 18):
+        o = Oracle(om, "bf16")
+        assert (np.stack([o.process(pcm[s, t]) for t in range(4)]) == out[s]).all()
+    assert OracleBatch(om, 19, "bf16").process(pcm[:, 0, :]).shape == (19, 256)
+
+
+def _rms(x):
+    return math.sqrt(float(np.mean((np.asarray(x, np.float64) / 32768.0) ** 2)))
+
+
+def _energy_test(model, mode, input_pcm, reference_pcm, tolerance=0.02):
+    """/root/reference/binding/python/test_koala.py:71-101, restated for an engine object with .process()."""
+    o = Oracle(model, mode)
+    fl, delay = o.frame_length, o.delay_sample
+    worst = 0.0
+    for start in range(0, len(input_pcm) - fl + 1, fl):
+        frame_energy = _rms(o.process(input_pcm[start:start + fl]))
+        if reference_pcm is None or start < delay:
+            dev = frame_energy
+        else:
+            dev = abs(frame_energy - _rms(reference_pcm[start - delay:start - delay + fl]))
+        worst = max(worst, dev)
+    assert worst < tolerance, worst
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_reference_behaviour_pure_speech(shipped, test_pcm, mode):
+    _energy_test(shipped, mode, test_pcm, test_pcm)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_reference_behaviour_pure_noise(shipped, noise_pcm, mode):
+    _energy_test(shipped, mode, noise_pcm, None)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_reference_behaviour_mixed(shipped, test_pcm, noise_pcm, mode):
+    noisy = np.clip(test_pcm.astype(np.int32) + noise_pcm.astype(np.int32), -32768, 32767).astype(np.int16)
+    _energy_test(shipped, mode, noisy, test_pcm)
+
+
+def test_fixture_facts(test_pcm, noise_pcm):
+    """both fixtures are 93 680 samples = 365 full frames + 240."""
+    assert len(test_pcm) == len(noise_pcm) == 93680
+    assert len(test_pcm) // 256 == 365
