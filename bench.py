@@ -218,7 +218,8 @@ def main():
     host_pcm = synth_pcm(streams, ring, seed=0x4B4F414C + rank)
     d_in = torch.from_numpy(host_pcm).to(dev)                     # [B][ring][256] resident in HBM
     d_out = torch.empty_like(d_in)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)                                # the launching stream: kernels AND timing events go here
+    torch.cuda.set_stream(stream)
     lib, handle = eng._library, eng._handle
     from ctypes import c_void_p
 

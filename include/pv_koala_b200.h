@@ -94,7 +94,8 @@ PV_API void pv_koala_batch_delete(pv_koala_batch_t *object);
 PV_API pv_status_t pv_koala_batch_process(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm, int32_t num_frames);
 
 /* Device buffers only, enqueue-only: frame t of stream s at base + s * stream_stride + t * 256 samples (16-byte aligned,
- * stride % 8 == 0).  cuda_stream: a cudaStream_t (NULL = the handle's own stream).  Pair with pv_koala_batch_synchronize. */
+ * stride % 8 == 0).  cuda_stream: a cudaStream_t passed as void* and taken literally (NULL = CUDA's legacy default stream).
+ * Work is ordered on that stream like any other kernel; pv_koala_batch_synchronize waits for the whole device. */
 PV_API pv_status_t pv_koala_batch_process_async(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,
                                                 int32_t num_frames, int64_t stream_stride, void *cuda_stream);
 PV_API pv_status_t pv_koala_batch_synchronize(pv_koala_batch_t *object);

@@ -13,6 +13,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "koala_common.cuh"
 #include "masknet_fp32.cuh"
 #include "masknet_tc.cuh"
@@ -97,7 +99,7 @@ Status load_model_file(const char *path, ModelHost *out, std::vector<std::string
 // ------------------------------------------------------------------------------------------------ engine
 struct Engine::Impl {
     cudaStream_t stream = nullptr;
-    int H = 0, L = 0;
+    int H = 0, L = 0, num_sms = 148;
     int parity = 0;   // h[parity] holds h(t-1)
     // model
     __nv_bfloat16 *enc_w = nullptr, *dec_w = nullptr, *wih[kMaxLayers] = {}, *whh[kMaxLayers] = {};
@@ -169,6 +171,7 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
     const size_t Bp = eng->npad_, H = model.hidden, L = model.layers;
     p->H = (int) H;
     p->L = (int) L;
+    p->num_sms = prop.multiProcessorCount;
     Status st = [&]() -> Status {
         KCHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
         KCHECK(upload(p->allocs, &p->enc_w, model.enc_w));
@@ -245,10 +248,10 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     }
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
-    cudaStream_t st = stream_ ? (cudaStream_t) stream_ : p->stream;
+    cudaStream_t st = (cudaStream_t) stream_;
     const int B = n_, Bp = npad_, H = p->H, L = p->L;
     const size_t LBH = (size_t) Bp * H;
-    const int stft_grid = (B + kStftWarps - 1) / kStftWarps;
+    const int stft_grid = std::min((B + kStftWarps - 1) / kStftWarps, 4 * p->num_sms);
     KernelProfiler *prof = p->prof;
     for (int t = 0; t < frames; t++) {
         PcmView v{pcm, out, stride, t};
@@ -308,7 +311,7 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
     }
     const size_t bytes = (size_t) n_ * frames * kFrame * sizeof(int16_t);
     KCHECK(cudaMemcpyAsync(p->d_in, pcm, bytes, cudaMemcpyHostToDevice, p->stream));
-    Status st = process_device(p->d_in, p->d_out, frames, (long long) frames * kFrame, nullptr, errors);
+    Status st = process_device(p->d_in, p->d_out, frames, (long long) frames * kFrame, p->stream, errors);
     if (st != kSuccess) return st;
     KCHECK(cudaMemcpyAsync(out, p->d_out, bytes, cudaMemcpyDeviceToHost, p->stream));
     KCHECK(cudaStreamSynchronize(p->stream));
@@ -394,9 +397,11 @@ Status Engine::profile_read(double *ms, long long *count, int n_classes, std::ve
     return kSuccess;
 }
 
+void *Engine::own_stream() const { return p_->stream; }
+
 Status Engine::synchronize(std::vector<std::string> *errors) {
     KCHECK(cudaSetDevice(device_));
-    KCHECK(cudaStreamSynchronize(p_->stream));
+    KCHECK(cudaDeviceSynchronize());
     return kSuccess;
 }
 

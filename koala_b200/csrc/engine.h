@@ -39,14 +39,15 @@ public:
     int precision() const { return precision_; }
 
     // pcm / out: frame t of stream s at base + s * stride + t * 256 (int16 samples).  Device pointers, 16-byte aligned,
-    // stride a multiple of 8.  Enqueues `frames` consecutive steps on `stream` (nullptr: the engine's own stream) and
-    // returns without synchronising.
+    // stride a multiple of 8.  Enqueues `frames` consecutive steps on `stream` (a cudaStream_t taken literally: nullptr is
+    // the legacy default stream; own_stream() is the engine's private one) and returns without synchronising.
     Status process_device(const int16_t *pcm, int16_t *out, int frames, long long stride, void *stream,
                           std::vector<std::string> *errors);
     // Host buffers [B][frames][256]: H2D copy, steps, D2H copy, synchronise.
     Status process_host(const int16_t *pcm, int16_t *out, int frames, std::vector<std::string> *errors);
     Status reset(const int32_t *stream_ids, int n, std::vector<std::string> *errors);   // ids == nullptr: all streams
-    Status synchronize(std::vector<std::string> *errors);
+    Status synchronize(std::vector<std::string> *errors);   // waits for everything queued on the device
+    void *own_stream() const;
 
     // test hooks: copy an internal tensor to the host ("feat", "spec", "mask", "h0", "h1", ..., "ola", "tail")
     Status debug_read(const char *name, void *dst, size_t bytes, std::vector<std::string> *errors);

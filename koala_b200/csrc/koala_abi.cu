@@ -354,7 +354,8 @@ PV_API pv_status_t pv_koala_batch_process(pv_koala_batch_t *object, const int16_
     std::vector<std::string> errs;
     Status st;
     if (kin == 1) {
-        st = object->engine->process_device(pcm, enhanced_pcm, num_frames, (long long) num_frames * koala::kFrame, nullptr, &errs);
+        st = object->engine->process_device(pcm, enhanced_pcm, num_frames, (long long) num_frames * koala::kFrame,
+                                            object->engine->own_stream(), &errs);
         if (st == koala::kSuccess) st = object->engine->synchronize(&errs);
     } else {
         st = object->engine->process_host(pcm, enhanced_pcm, num_frames, &errs);

@@ -11,7 +11,7 @@
 
 namespace koala {
 
-constexpr int kStftWarps = 4;
+constexpr int kStftWarps = 8;
 constexpr int kTableBytes = 4096;   // float window[512] | float2 twiddle[256]
 
 template <typename FeatT> __device__ __forceinline__ void store_feat8(FeatT *dst, const float (&f)[8]);
@@ -28,7 +28,9 @@ template <> __device__ __forceinline__ void store_feat8<__nv_bfloat16>(__nv_bflo
     *reinterpret_cast<uint4 *>(dst) = u;
 }
 
-// grid = ceil(n_streams / 4), block = 128.  spec: [n][512] fp32 packed (Re,Im of bins 0..255, Im slot of bin 0 = Re X[256]).
+// Persistent-style launch: grid = min(ceil(n / 8), 4 CTAs per SM), block = 256; each warp walks streams
+// s = blockIdx * 8 + warp, += gridDim * 8, so the lookup tables are staged once per CTA.
+// spec: [n][512] fp32 packed (Re, Im of bins 0..255; the Im slot of bin 0 carries Re X[256]).
 template <typename FeatT>
 __global__ void __launch_bounds__(kStftWarps * 32)
 frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__restrict__ spec,
@@ -47,64 +49,70 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
         mbar_expect_tx(&s_bar, kTableBytes);
         bulk_g2s(s_tab, tables, kTableBytes, &s_bar);
     }
-    const int s = blockIdx.x * kStftWarps + warp;
-    const bool active = s < n_streams;
-    if (active) {
-        // frame = [previous input frame | this input frame]; lanes 0-15 fetch the tail, 16-31 the new samples (16 B each)
-        int16_t *tail_s = tail + (size_t) s * kFrame;
-        const int16_t *src = lane < 16 ? tail_s + lane * 8
-                                       : v.in + (size_t) s * v.stride + (size_t) v.t * kFrame + (lane - 16) * 8;
-        const uint4 d = *reinterpret_cast<const uint4 *>(src);
-        *reinterpret_cast<uint4 *>(&s_frame[warp][lane * 8]) = d;
-        if (lane >= 16) *reinterpret_cast<uint4 *>(tail_s + (lane - 16) * 8) = d;   // state: tail <- this frame
-    }
-    __syncwarp();
     mbar_wait(&s_bar, 0);
-    if (!active) return;
 
     const float2 *win2 = reinterpret_cast<const float2 *>(s_tab);
     const float2 *tw = reinterpret_cast<const float2 *>(s_tab + kNfft);
     const uint32_t *fw = reinterpret_cast<const uint32_t *>(s_frame[warp]);
-    cpx z[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int p = lane + 32 * j;
-        const uint32_t u = fw[p];
-        const float2 w = win2[p];
-        z[j] = cpx{w.x * (float) (int16_t) (u & 0xffffu), w.y * (float) (int16_t) (u >> 16)};
-    }
-    warp_fft256_dif(z, tw, lane);
-
-    // real-FFT split: X[k] = E + W512^k O,  E = (Z[k] + conj Z[256-k]) / 2,  O = (Z[k] - conj Z[256-k]) / 2i
     const int a = rev5(lane);
     const int src_a = rev5((32 - a) & 31), src_b = 31 - lane;
-    cpx X[8];
+
+    for (int s = blockIdx.x * kStftWarps + warp; s < n_streams; s += gridDim.x * kStftWarps) {
+        // frame = [previous input frame | this input frame], 1024 bytes: lanes 0-15 fetch 32 B of the tail each,
+        // lanes 16-31 32 B of the new samples (two 16-byte vector loads per lane)
+        int16_t *tail_s = tail + (size_t) s * kFrame;
+        const int16_t *src = lane < 16 ? tail_s + lane * 16
+                                       : v.in + (size_t) s * v.stride + (size_t) v.t * kFrame + (lane - 16) * 16;
+        const uint4 d0 = reinterpret_cast<const uint4 *>(src)[0];
+        const uint4 d1 = reinterpret_cast<const uint4 *>(src)[1];
+        __syncwarp();   // previous iteration's reads of s_frame are done
+        reinterpret_cast<uint4 *>(&s_frame[warp][lane * 16])[0] = d0;
+        reinterpret_cast<uint4 *>(&s_frame[warp][lane * 16])[1] = d1;
+        if (lane >= 16) {   // state: tail <- this frame (issued after the loads above have returned for the whole warp)
+            reinterpret_cast<uint4 *>(tail_s + (lane - 16) * 16)[0] = d0;
+            reinterpret_cast<uint4 *>(tail_s + (lane - 16) * 16)[1] = d1;
+        }
+        __syncwarp();
+
+        cpx z[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int b = rev3c(j);
-        const cpx zk = z[j];
-        const cpx zp = shfl_c(z[partner_reg(j)], j == 0 ? src_a : src_b);
-        const cpx E = {0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y)};
-        const cpx O = {0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x)};
-        const float2 w = tw[8 * a + b];
-        cpx x = cadd(E, cmul(O, cpx{w.x, w.y}));
-        if (j == 0 && lane == 0) x = cpx{zk.x + zk.y, zk.x - zk.y};   // (X[0], X[256]), both real
-        X[b] = x;
+        for (int j = 0; j < 8; ++j) {
+            const int p = lane + 32 * j;
+            const uint32_t u = fw[p];
+            const float2 w = win2[p];
+            z[j] = cpx{w.x * (float) (int16_t) (u & 0xffffu), w.y * (float) (int16_t) (u >> 16)};
+        }
+        warp_fft256_dif(z, tw, lane);
+
+        // real-FFT split: X[k] = E + W512^k O,  E = (Z[k] + conj Z[256-k]) / 2,  O = (Z[k] - conj Z[256-k]) / 2i
+        cpx X[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int b = rev3c(j);
+            const cpx zk = z[j];
+            const cpx zp = shfl_c(z[partner_reg(j)], j == 0 ? src_a : src_b);
+            const cpx E = {0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y)};
+            const cpx O = {0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x)};
+            const float2 w = tw[8 * a + b];
+            cpx x = cadd(E, cmul(O, cpx{w.x, w.y}));
+            if (j == 0 && lane == 0) x = cpx{zk.x + zk.y, zk.x - zk.y};   // (X[0], X[256]), both real
+            X[b] = x;
+        }
+        float f[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const float im = (b == 0 && lane == 0) ? 0.0f : X[b].y;
+            const float p = (X[b].x * X[b].x + im * im) * kFeatPowerScale;
+            f[b] = kFeatGain * __logf(p + kFeatEps) + kFeatBias;
+        }
+        float4 *sp = reinterpret_cast<float4 *>(spec + (size_t) s * kNfft + 16 * a);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sp[q] = make_float4(X[2 * q].x, X[2 * q].y, X[2 * q + 1].x, X[2 * q + 1].y);
+        store_feat8<FeatT>(feat + (size_t) s * kBins + 8 * a, f);
     }
-    float f[8];
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        const float im = (b == 0 && lane == 0) ? 0.0f : X[b].y;
-        const float p = (X[b].x * X[b].x + im * im) * kFeatPowerScale;
-        f[b] = kFeatGain * __logf(p + kFeatEps) + kFeatBias;
-    }
-    float4 *sp = reinterpret_cast<float4 *>(spec + (size_t) s * kNfft + 16 * a);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) sp[q] = make_float4(X[2 * q].x, X[2 * q].y, X[2 * q + 1].x, X[2 * q + 1].y);
-    store_feat8<FeatT>(feat + (size_t) s * kBins + 8 * a, f);
 }
 
-// grid = ceil(n_streams / 4), block = 128.  mask: [n][256] fp32.  ola: [n][256] fp32 state.
+// Same launch shape as frontend_kernel.  mask: [n][256] fp32.  ola: [n][256] fp32 state.
 __global__ void __launch_bounds__(kStftWarps * 32)
 backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const float *__restrict__ mask,
                float *__restrict__ ola, const float *__restrict__ tables) {
@@ -121,12 +129,17 @@ backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const f
         mbar_expect_tx(&s_bar, kTableBytes);
         bulk_g2s(s_tab, tables, kTableBytes, &s_bar);
     }
-    const int s = blockIdx.x * kStftWarps + warp;
-    const bool active = s < n_streams;
+    mbar_wait(&s_bar, 0);
+
+    const float2 *win2 = reinterpret_cast<const float2 *>(s_tab);
+    const float2 *tw = reinterpret_cast<const float2 *>(s_tab + kNfft);
     const int a = rev5(lane);
-    cpx Y[8];
-    float m[8];
-    if (active) {
+    const int src_a = rev5((32 - a) & 31), src_b = 31 - lane;
+    constexpr float inv = 1.0f / 256.0f;
+
+    for (int s = blockIdx.x * kStftWarps + warp; s < n_streams; s += gridDim.x * kStftWarps) {
+        cpx Y[8];
+        float m[8];
         const float4 *sp = reinterpret_cast<const float4 *>(spec + (size_t) s * kNfft + 16 * a);
         const float4 *mp = reinterpret_cast<const float4 *>(mask + (size_t) s * kBins + 8 * a);
 #pragma unroll
@@ -138,55 +151,48 @@ backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const f
         const float4 m0 = mp[0], m1 = mp[1];
         m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w;
         m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
-    }
-    mbar_wait(&s_bar, 0);
-    if (!active) return;
+        const float m255 = __shfl_sync(0xffffffffu, m[7], 31);   // lane 31 holds bins 248..255
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            Y[b].x *= m[b];
+            Y[b].y *= (b == 0 && lane == 0) ? m255 : m[b];       // lane 0, b 0: Im slot carries X[256], masked by mask[255]
+        }
+        // inverse split: Z[k] = E + i O,  E = (Y[k] + conj Y[256-k]) / 2,  O = (Y[k] - conj Y[256-k]) / 2 * conj(W512^k)
+        cpx z[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int b = rev3c(j), bp = (8 - b) & 7;
+            const cpx yk = Y[b];
+            const cpx yp = shfl_c(Y[bp], j == 0 ? src_a : src_b);
+            const cpx E = {0.5f * (yk.x + yp.x), 0.5f * (yk.y - yp.y)};
+            const cpx D = {0.5f * (yk.x - yp.x), 0.5f * (yk.y + yp.y)};
+            const float2 w = tw[8 * a + b];
+            const cpx O = cmulc(D, cpx{w.x, w.y});
+            cpx zz = {E.x - O.y, E.y + O.x};
+            if (j == 0 && lane == 0) zz = cpx{0.5f * (yk.x + yk.y), 0.5f * (yk.x - yk.y)};
+            z[j] = zz;
+        }
+        warp_ifft256_dit(z, tw, lane);
 
-    const float2 *win2 = reinterpret_cast<const float2 *>(s_tab);
-    const float2 *tw = reinterpret_cast<const float2 *>(s_tab + kNfft);
-    const float m255 = __shfl_sync(0xffffffffu, m[7], 31);   // lane 31 holds bins 248..255
+        // z[j] = 256 (y[2p] + i y[2p+1]), p = lane + 32 j.  j < 4: first half -> output; j >= 4: second half -> new OLA tail.
+        float2 *ola2 = reinterpret_cast<float2 *>(ola + (size_t) s * kFrame);
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(v.out + (size_t) s * v.stride + (size_t) v.t * kFrame);
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        Y[b].x *= m[b];
-        Y[b].y *= (b == 0 && lane == 0) ? m255 : m[b];       // lane 0, b 0: Im slot carries X[256], masked by mask[255]
-    }
-    // inverse split: Z[k] = E + i O,  E = (Y[k] + conj Y[256-k]) / 2,  O = (Y[k] - conj Y[256-k]) / 2 * conj(W512^k)
-    const int src_a = rev5((32 - a) & 31), src_b = 31 - lane;
-    cpx z[8];
+        for (int j = 0; j < 4; ++j) {
+            const int p = lane + 32 * j;
+            const float2 w = win2[p], o = ola2[p];
+            const float v0 = o.x + w.x * (z[j].x * inv), v1 = o.y + w.y * (z[j].y * inv);
+            short i0, i1;   // round-to-nearest-even + saturate, the oracle's rintf + clamp
+            asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i0) : "f"(v0));
+            asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i1) : "f"(v1));
+            out32[p] = (uint32_t) (uint16_t) i0 | ((uint32_t) (uint16_t) i1 << 16);
+        }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int b = rev3c(j), bp = (8 - b) & 7;
-        const cpx yk = Y[b];
-        const cpx yp = shfl_c(Y[bp], j == 0 ? src_a : src_b);
-        const cpx E = {0.5f * (yk.x + yp.x), 0.5f * (yk.y - yp.y)};
-        const cpx D = {0.5f * (yk.x - yp.x), 0.5f * (yk.y + yp.y)};
-        const float2 w = tw[8 * a + b];
-        const cpx O = cmulc(D, cpx{w.x, w.y});
-        cpx zz = {E.x - O.y, E.y + O.x};
-        if (j == 0 && lane == 0) zz = cpx{0.5f * (yk.x + yk.y), 0.5f * (yk.x - yk.y)};
-        z[j] = zz;
-    }
-    warp_ifft256_dit(z, tw, lane);
-
-    // z[j] = 256 * (y[2p] + i y[2p+1]), p = lane + 32 j.  j < 4: first half -> output; j >= 4: second half -> new OLA tail.
-    constexpr float inv = 1.0f / 256.0f;
-    float2 *ola2 = reinterpret_cast<float2 *>(ola + (size_t) s * kFrame);
-    uint32_t *out32 = reinterpret_cast<uint32_t *>(v.out + (size_t) s * v.stride + (size_t) v.t * kFrame);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int p = lane + 32 * j;
-        const float2 w = win2[p], o = ola2[p];
-        const float v0 = o.x + w.x * (z[j].x * inv), v1 = o.y + w.y * (z[j].y * inv);
-        short i0, i1;   // round-to-nearest-even + saturate, the oracle's rintf + clamp
-        asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i0) : "f"(v0));
-        asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i1) : "f"(v1));
-        out32[p] = (uint32_t) (uint16_t) i0 | ((uint32_t) (uint16_t) i1 << 16);
-    }
-#pragma unroll
-    for (int j = 4; j < 8; ++j) {
-        const int p = lane + 32 * j;
-        const float2 w = win2[p];
-        ola2[p - 128] = make_float2(w.x * (z[j].x * inv), w.y * (z[j].y * inv));
+        for (int j = 4; j < 8; ++j) {
+            const int p = lane + 32 * j;
+            const float2 w = win2[p];
+            ola2[p - 128] = make_float2(w.x * (z[j].x * inv), w.y * (z[j].y * inv));
+        }
     }
 }
 
