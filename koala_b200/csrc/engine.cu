@@ -104,7 +104,7 @@ struct Engine::Impl {
     // model
     __nv_bfloat16 *enc_w = nullptr, *dec_w = nullptr, *wih[kMaxLayers] = {}, *whh[kMaxLayers] = {};
     float *enc_b = nullptr, *dec_b = nullptr, *bih[kMaxLayers] = {}, *bhh[kMaxLayers] = {};
-    float *tables = nullptr;
+    float2 *tables = nullptr;   // lane-major FFT constants
     // state
     int16_t *tail = nullptr;
     float *ola = nullptr;
@@ -184,12 +184,26 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             KCHECK(upload(p->allocs, &p->bih[l], model.bih[l]));
             KCHECK(upload(p->allocs, &p->bhh[l], model.bhh[l]));
         }
-        std::vector<float> tab(kTableBytes / 4);
-        for (int i = 0; i < kNfft; i++) tab[i] = (float) sin(M_PI * (double) i / kNfft);
-        for (int k = 0; k < kNfft / 2; k++) {
+        // lane-major constants of the warp FFT (FftLane in koala_common.cuh): float2 [27][32], all computed in double
+        std::vector<float2> tab((size_t) kLaneTabRows * 32);
+        auto tw = [](int k) {
             const double a = -2.0 * M_PI * (double) k / kNfft;
-            tab[kNfft + 2 * k] = (float) cos(a);
-            tab[kNfft + 2 * k + 1] = (float) sin(a);
+            return make_float2((float) cos(a), (float) sin(a));
+        };
+        auto rev5h = [](int v) { int r = 0; for (int b = 0; b < 5; b++) r |= ((v >> b) & 1) << (4 - b); return r; };
+        for (int lane = 0; lane < 32; lane++) {
+            for (int q = 0; q < 4; q++) tab[(0 + q) * 32 + lane] = tw((lane + 32 * q) * 2);
+            for (int q = 0; q < 2; q++) tab[(4 + q) * 32 + lane] = tw((lane + 32 * q) * 4);
+            tab[6 * 32 + lane] = tw(lane * 8);
+            for (int s = 0; s < 4; s++) {
+                const int h = 16 >> s;
+                tab[(7 + s) * 32 + lane] = tw((lane & (h - 1)) * (256 / h));
+            }
+            for (int b = 0; b < 8; b++) tab[(11 + b) * 32 + lane] = tw(8 * rev5h(lane) + b);
+            for (int j = 0; j < 8; j++) {
+                const int p2 = 2 * (lane + 32 * j);
+                tab[(19 + j) * 32 + lane] = make_float2((float) sin(M_PI * (double) p2 / kNfft), (float) sin(M_PI * (double) (p2 + 1) / kNfft));
+            }
         }
         KCHECK(upload(p->allocs, &p->tables, tab));
         KCHECK(dev_alloc(p->allocs, &p->tail, Bp * kFrame));
@@ -251,7 +265,7 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     cudaStream_t st = (cudaStream_t) stream_;
     const int B = n_, Bp = npad_, H = p->H, L = p->L;
     const size_t LBH = (size_t) Bp * H;
-    const int stft_grid = std::min((B + kStftWarps - 1) / kStftWarps, 4 * p->num_sms);
+    const int stft_grid = std::min((B + kStftWarps - 1) / kStftWarps, 2 * p->num_sms);
     KernelProfiler *prof = p->prof;
     for (int t = 0; t < frames; t++) {
         PcmView v{pcm, out, stride, t};

@@ -91,55 +91,81 @@ __device__ __forceinline__ cpx shfl_c(cpx v, int src) {
 }
 __device__ __forceinline__ int rev5(int v) { return (int) (__brev((unsigned) v) >> 27); }
 
+// Per-lane constants of the warp FFT, held in registers for every stream a warp processes.  The host lays them out
+// lane-major (float2 [kLaneTabRows][32]) so that loading them is one coalesced 256-byte request per row and there is no
+// shared-memory twiddle traffic inside the stream loop (the first version read twiddles from shared memory with up to
+// 16-way bank conflicts and was LSU-bound: profiles/r01_step_summary.md).
+constexpr int kLaneTabRows = 27;
+struct FftLane {
+    float2 t4[4];    // span 128: W512^{2 (lane + 32 q)},  q = j & 3
+    float2 t2[2];    // span  64: W512^{4 (lane + 32 q)},  q = j & 1
+    float2 t1;       // span  32: W512^{8 lane}
+    float2 tx[4];    // spans 16, 8, 4, 2 (lane exchange): W512^{(lane & (h-1)) * 256 / h}
+    float2 tp[8];    // real-FFT split: W512^{8 rev5(lane) + b}
+    float2 win[8];   // sqrt-Hann window pairs (w[2p], w[2p+1]), p = lane + 32 j
+};
+__device__ __forceinline__ void load_fft_lane(FftLane &c, const float2 *__restrict__ tab, int lane) {
+    const float2 *t = tab + lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c.t4[i] = __ldg(t + 32 * i);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) c.t2[i] = __ldg(t + 32 * (4 + i));
+    c.t1 = __ldg(t + 32 * 6);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c.tx[i] = __ldg(t + 32 * (7 + i));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.tp[i] = __ldg(t + 32 * (11 + i));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.win[i] = __ldg(t + 32 * (19 + i));
+}
+
 // One warp = one 256-point complex FFT.  Lane l, register j hold element p = l + 32 j.
 // Forward: radix-2 DIF, natural order in -> bit-reversed out: after the call z[j] = Z[8 * rev5(lane) + rev3(j)].
-// tw[k] = exp(-2 pi i k / 512), k = 0..255 (float2 in shared memory).
-__device__ __forceinline__ void warp_fft256_dif(cpx (&z)[8], const float2 *tw, int lane) {
+__device__ __forceinline__ void warp_fft256_dif(cpx (&z)[8], const FftLane &c, int lane) {
 #pragma unroll
     for (int dj = 4; dj >= 1; dj >>= 1) {   // spans 128, 64, 32: partner is another register of the same lane
-        const int mul = 8 / dj;             // 256 / span
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (j & dj) continue;
-            const float2 w2 = tw[(lane + 32 * (j % dj)) * mul];
+            const float2 w2 = dj == 4 ? c.t4[j & 3] : dj == 2 ? c.t2[j & 1] : c.t1;
             const cpx a = z[j], b = z[j + dj];
             z[j] = cadd(a, b);
             z[j + dj] = cmul(csub(a, b), cpx{w2.x, w2.y});
         }
     }
 #pragma unroll
-    for (int h = 16; h >= 1; h >>= 1) {     // spans 16..1: partner is lane ^ h
-        const float2 w2 = tw[(lane & (h - 1)) * (256 / h)];
+    for (int s = 0; s < 5; ++s) {           // spans 16..1: partner is lane ^ h
+        const int h = 16 >> s;
         const bool up = (lane & h) != 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const cpx v = z[j], o = shfl_xor_c(v, h);
-            z[j] = up ? cmul(csub(o, v), cpx{w2.x, w2.y}) : cadd(v, o);
+            if (s < 4) z[j] = up ? cmul(csub(o, v), cpx{c.tx[s].x, c.tx[s].y}) : cadd(v, o);
+            else z[j] = up ? csub(o, v) : cadd(v, o);   // span 1: twiddle is 1
         }
     }
 }
 
 // Inverse: radix-2 DIT with conjugate twiddles, bit-reversed in (layout produced by warp_fft256_dif) -> natural out.
 // No 1/256 scaling is applied.
-__device__ __forceinline__ void warp_ifft256_dit(cpx (&z)[8], const float2 *tw, int lane) {
+__device__ __forceinline__ void warp_ifft256_dit(cpx (&z)[8], const FftLane &c, int lane) {
 #pragma unroll
-    for (int h = 1; h <= 16; h <<= 1) {
-        const float2 w2 = tw[(lane & (h - 1)) * (256 / h)];
+    for (int s = 4; s >= 0; --s) {          // spans 1, 2, 4, 8, 16
+        const int h = 16 >> s;
         const bool up = (lane & h) != 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const cpx t = up ? cmulc(z[j], cpx{w2.x, w2.y}) : z[j];
+            const cpx t = (up && s < 4) ? cmulc(z[j], cpx{c.tx[s < 4 ? s : 0].x, c.tx[s < 4 ? s : 0].y}) : z[j];
             const cpx o = shfl_xor_c(t, h);
             z[j] = up ? csub(o, t) : cadd(t, o);
         }
     }
 #pragma unroll
     for (int dj = 1; dj <= 4; dj <<= 1) {
-        const int mul = 8 / dj;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (j & dj) continue;
-            const float2 w2 = tw[(lane + 32 * (j % dj)) * mul];
+            const float2 w2 = dj == 4 ? c.t4[j & 3] : dj == 2 ? c.t2[j & 1] : c.t1;
             const cpx a = z[j], b = cmulc(z[j + dj], cpx{w2.x, w2.y});
             z[j] = cadd(a, b);
             z[j + dj] = csub(a, b);

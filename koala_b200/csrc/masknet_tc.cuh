@@ -5,8 +5,8 @@
 // bf16 operands staged by TMA into 128B-swizzled shared memory, tcgen05.mma (cta_group::1, M = 128) accumulating fp32
 // in TMEM, gates / state update / activation fused into the epilogue that reads TMEM back with tcgen05.ld.
 //
-// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-// (one TMEM lane quarter each).  Two accumulator buffers of 256 TMEM columns let the epilogue of tile i overlap the MMAs
+// One persistent CTA per SM, 10 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+// (two warps per TMEM lane quarter, splitting the columns; the first version had 4 epilogue warps and was epilogue-bound).  Two accumulator buffers of 256 TMEM columns let the epilogue of tile i overlap the MMAs
 // of tile i+1.
 //
 // GRU tile = 128 streams x 64 hidden units.  TMEM columns: [r 0..63 | z 64..127 | n_x 128..191 | n_h 192..255].
@@ -29,8 +29,8 @@ constexpr int kTcStages = 4;
 constexpr int kTcABytes = kTcBlockM * 128;    // 16 KB
 constexpr int kTcBBytesMax = 256 * 128;       // 32 KB
 constexpr int kTcStageBytes = kTcABytes + kTcBBytesMax;
-constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kTcThreads = 192;
+constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*biases*/;
+constexpr int kTcThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kTcAccCols = 256;
 constexpr int kGruUnits = 64;                 // hidden units per GRU tile
 constexpr int kGruRows = 3 * kGruUnits;       // packed weight rows per tile
@@ -130,6 +130,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     uint64_t *full_bar = bars, *empty_bar = bars + kTcStages;
     uint64_t *tmem_full = bars + 2 * kTcStages, *tmem_empty = bars + 2 * kTcStages + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTcStages + 4);
+    float *s_bias = reinterpret_cast<float *>(smem + kTcStages * kTcStageBytes + 256);   // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -145,7 +146,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], 128);
+            mbar_init(&tmem_empty[b], 256);
         }
         fence_mbar_init();
     }
@@ -210,70 +211,86 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
         }
     } else {
-        // ===================================================== epilogue (warps 2..5 -> TMEM lane quarter warp % 4)
-        const int quarter = warp & 3;
+        // ===================================================== epilogue: warps 2..9; TMEM lane quarter = warp % 4, the two
+        // warps of a quarter split the columns (GRU: 32 of the 64 units each; linear: 128 of the 256 outputs each)
+        const int quarter = warp & 3, half = (warp - 2) >> 2, te = threadIdx.x - 64;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m = tile / args.num_n_tiles, n = tile % args.num_n_tiles;
             const int ab = it & 1, aphase = (it >> 1) & 1;
+            const size_t row = (size_t) m * kTcBlockM + quarter * 32 + lane;
+            float *sb = s_bias + ab * 256;
+            float hp[32];
+            if (kGru) {
+                // biases of this tile -> smem ([r | z | n_x | n_h] x 64), previous state of my 32 units -> registers;
+                // both are independent of the MMAs, so they are fetched before waiting for the accumulator
+                const int H = args.H, g = te >> 6, u = n * kGruUnits + (te & 63);
+                sb[te] = g == 0 ? __ldg(args.bias0 + u) + __ldg(args.bias1 + u)
+                       : g == 1 ? __ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u)
+                       : g == 2 ? __ldg(args.bias0 + 2 * H + u) : __ldg(args.bias1 + 2 * H + u);
+                const float4 *hp4 = reinterpret_cast<const float4 *>(args.h_prev + row * H + n * kGruUnits + half * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 t = hp4[q];
+                    hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
+                }
+            } else {
+                sb[te] = __ldg(args.bias0 + n * 256 + te);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the 256 epilogue threads only
             mbar_wait(&tmem_full[ab], aphase);
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t) (quarter * 32) << 16) + ab * kTcAccCols;
-            const size_t row = (size_t) m * kTcBlockM + quarter * 32 + lane;
             if (kGru) {
                 const int H = args.H;
-#pragma unroll 1
-                for (int c = 0; c < kGruUnits / 16; ++c) {
-                    float ar[16], az[16], anx[16], anh[16];
-                    tmem_ld16(t0 + 0 + c * 16, ar);
-                    tmem_ld16(t0 + 64 + c * 16, az);
-                    tmem_ld16(t0 + 128 + c * 16, anx);
-                    tmem_ld16(t0 + 192 + c * 16, anh);
-                    const int u0 = n * kGruUnits + c * 16;
-                    float hp[16], hn[16];
-                    const float4 *hp4 = reinterpret_cast<const float4 *>(args.h_prev + row * H + u0);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 t = hp4[q];
-                        hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
-                    }
+                for (int c = 0; c < 2; ++c) {
+                    const int cu = half * 32 + c * 16;           // first unit of this chunk inside the tile
+                    float ar[16], az[16], anx[16], anh[16], hn[16];
+                    tmem_ld16(t0 + 0 + cu, ar);
+                    tmem_ld16(t0 + 64 + cu, az);
+                    tmem_ld16(t0 + 128 + cu, anx);
+                    tmem_ld16(t0 + 192 + cu, anh);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int u = u0 + i;
-                        const float br = __ldg(args.bias0 + u) + __ldg(args.bias1 + u);
-                        const float bz = __ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u);
-                        const float rg = sigmoid_f(ar[i] + br);
-                        const float zg = sigmoid_f(az[i] + bz);
-                        const float ng = tanh_f(anx[i] + __ldg(args.bias0 + 2 * H + u) + rg * (anh[i] + __ldg(args.bias1 + 2 * H + u)));
-                        hn[i] = (1.0f - zg) * ng + zg * hp[i];
+                        // r = 1/(1+er), z = 1/(1+ez) with one shared reciprocal: 5 MUFU ops per unit instead of 6
+                        const float er = __expf(fminf(-(ar[i] + sb[cu + i]), 30.0f));
+                        const float ez = __expf(fminf(-(az[i] + sb[64 + cu + i]), 30.0f));
+                        const float pr = 1.0f + er, pz = 1.0f + ez;
+                        const float ip = __fdividef(1.0f, pr * pz);
+                        const float rg = pz * ip, zg = pr * ip;
+                        const float ng = tanh_f(anx[i] + sb[128 + cu + i] + rg * (anh[i] + sb[192 + cu + i]));
+                        hn[i] = (1.0f - zg) * ng + zg * hp[c * 16 + i];
                     }
-                    float4 *ho4 = reinterpret_cast<float4 *>(args.h_next + row * H + u0);
+                    const size_t off = row * H + n * kGruUnits + cu;
+                    float4 *ho4 = reinterpret_cast<float4 *>(args.h_next + off);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) ho4[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
-                    uint4 *hb4 = reinterpret_cast<uint4 *>(args.out_bf16 + row * H + u0);
+                    uint4 *hb4 = reinterpret_cast<uint4 *>(args.out_bf16 + off);
                     hb4[0] = pack_bf16x8(hn);
                     hb4[1] = pack_bf16x8(hn + 8);
                 }
             } else {
                 const int N = args.num_n_tiles * 256;
-#pragma unroll 1
-                for (int c = 0; c < 256 / 16; ++c) {
+#pragma unroll 2
+                for (int c = 0; c < 8; ++c) {
+                    const int cc = half * 128 + c * 16;
                     float acc[16];
-                    tmem_ld16(t0 + c * 16, acc);
+                    tmem_ld16(t0 + cc, acc);
                     tmem_ld_wait();
-                    const int n0 = n * 256 + c * 16;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float v = acc[i] + __ldg(args.bias0 + n0 + i);
+                        const float v = acc[i] + sb[cc + i];
                         acc[i] = MODE == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
                     }
+                    const size_t off = row * N + n * 256 + cc;
                     if (MODE == kTcEnc) {
-                        uint4 *o = reinterpret_cast<uint4 *>(args.out_bf16 + row * N + n0);
+                        uint4 *o = reinterpret_cast<uint4 *>(args.out_bf16 + off);
                         o[0] = pack_bf16x8(acc);
                         o[1] = pack_bf16x8(acc + 8);
                     } else {
-                        float4 *o = reinterpret_cast<float4 *>(args.out_f32 + row * N + n0);
+                        float4 *o = reinterpret_cast<float4 *>(args.out_f32 + off);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
                     }

@@ -2,9 +2,10 @@
 //
 // These are the first and last stage of `pv_koala_process` (/root/reference/include/pv_koala.h:65-80; stage names from
 // BASELINE.json north_star; the reference's own versions exist only as sm_61 SASS, SURVEY.md section 2.1 taabe228/151/7).
-// One warp owns one stream-frame: a 512-point real FFT is done as a 256-point complex FFT held 8 points per lane,
-// 3 radix-2 stages in registers and 5 by warp shuffles, followed by the real-FFT split (also by shuffles).
-// HBM-bound stages: 16-byte vector loads of packed int16 PCM, lookup tables staged once per CTA by a 1-D bulk copy.
+// One warp owns one stream-frame at a time: a 512-point real FFT is done as a 256-point complex FFT held 8 points per
+// lane, 3 radix-2 stages in registers and 5 by warp shuffles, followed by the real-FFT split (also by shuffles).
+// HBM-bound stages by bytes, LSU-bound in practice (shuffles): window and twiddles live in registers for all streams a
+// warp walks, PCM moves with 16-byte vector loads, outputs leave as full 128-byte lines.
 #pragma once
 
 #include "koala_common.cuh"
@@ -12,7 +13,6 @@
 namespace koala {
 
 constexpr int kStftWarps = 8;
-constexpr int kTableBytes = 4096;   // float window[512] | float2 twiddle[256]
 
 template <typename FeatT> __device__ __forceinline__ void store_feat8(FeatT *dst, const float (&f)[8]);
 template <> __device__ __forceinline__ void store_feat8<float>(float *dst, const float (&f)[8]) {
@@ -28,31 +28,18 @@ template <> __device__ __forceinline__ void store_feat8<__nv_bfloat16>(__nv_bflo
     *reinterpret_cast<uint4 *>(dst) = u;
 }
 
-// Persistent-style launch: grid = min(ceil(n / 8), 4 CTAs per SM), block = 256; each warp walks streams
-// s = blockIdx * 8 + warp, += gridDim * 8, so the lookup tables are staged once per CTA.
+// Persistent-style launch: grid = min(ceil(n / 8), 2 CTAs per SM), block = 256; each warp walks streams
+// s = blockIdx * 8 + warp, += gridDim * 8.
 // spec: [n][512] fp32 packed (Re, Im of bins 0..255; the Im slot of bin 0 carries Re X[256]).
 template <typename FeatT>
 __global__ void __launch_bounds__(kStftWarps * 32)
 frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__restrict__ spec,
-                FeatT *__restrict__ feat, const float *__restrict__ tables) {
-    __shared__ __align__(128) float s_tab[kTableBytes / 4];
+                FeatT *__restrict__ feat, const float2 *__restrict__ lane_tab) {
     __shared__ __align__(16) int16_t s_frame[kStftWarps][kNfft];
-    __shared__ __align__(8) uint64_t s_bar;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&s_bar, kTableBytes);
-        bulk_g2s(s_tab, tables, kTableBytes, &s_bar);
-    }
-    mbar_wait(&s_bar, 0);
-
-    const float2 *win2 = reinterpret_cast<const float2 *>(s_tab);
-    const float2 *tw = reinterpret_cast<const float2 *>(s_tab + kNfft);
+    FftLane c;
+    load_fft_lane(c, lane_tab, lane);
     const uint32_t *fw = reinterpret_cast<const uint32_t *>(s_frame[warp]);
     const int a = rev5(lane);
     const int src_a = rev5((32 - a) & 31), src_b = 31 - lane;
@@ -77,12 +64,10 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
         cpx z[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int p = lane + 32 * j;
-            const uint32_t u = fw[p];
-            const float2 w = win2[p];
-            z[j] = cpx{w.x * (float) (int16_t) (u & 0xffffu), w.y * (float) (int16_t) (u >> 16)};
+            const uint32_t u = fw[lane + 32 * j];
+            z[j] = cpx{c.win[j].x * (float) (int16_t) (u & 0xffffu), c.win[j].y * (float) (int16_t) (u >> 16)};
         }
-        warp_fft256_dif(z, tw, lane);
+        warp_fft256_dif(z, c, lane);
 
         // real-FFT split: X[k] = E + W512^k O,  E = (Z[k] + conj Z[256-k]) / 2,  O = (Z[k] - conj Z[256-k]) / 2i
         cpx X[8];
@@ -93,8 +78,7 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
             const cpx zp = shfl_c(z[partner_reg(j)], j == 0 ? src_a : src_b);
             const cpx E = {0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y)};
             const cpx O = {0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x)};
-            const float2 w = tw[8 * a + b];
-            cpx x = cadd(E, cmul(O, cpx{w.x, w.y}));
+            cpx x = cadd(E, cmul(O, cpx{c.tp[b].x, c.tp[b].y}));
             if (j == 0 && lane == 0) x = cpx{zk.x + zk.y, zk.x - zk.y};   // (X[0], X[256]), both real
             X[b] = x;
         }
@@ -115,24 +99,10 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
 // Same launch shape as frontend_kernel.  mask: [n][256] fp32.  ola: [n][256] fp32 state.
 __global__ void __launch_bounds__(kStftWarps * 32)
 backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const float *__restrict__ mask,
-               float *__restrict__ ola, const float *__restrict__ tables) {
-    __shared__ __align__(128) float s_tab[kTableBytes / 4];
-    __shared__ __align__(8) uint64_t s_bar;
-
+               float *__restrict__ ola, const float2 *__restrict__ lane_tab) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&s_bar, kTableBytes);
-        bulk_g2s(s_tab, tables, kTableBytes, &s_bar);
-    }
-    mbar_wait(&s_bar, 0);
-
-    const float2 *win2 = reinterpret_cast<const float2 *>(s_tab);
-    const float2 *tw = reinterpret_cast<const float2 *>(s_tab + kNfft);
+    FftLane c;
+    load_fft_lane(c, lane_tab, lane);
     const int a = rev5(lane);
     const int src_a = rev5((32 - a) & 31), src_b = 31 - lane;
     constexpr float inv = 1.0f / 256.0f;
@@ -151,6 +121,12 @@ backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const f
         const float4 m0 = mp[0], m1 = mp[1];
         m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w;
         m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+        // OLA tail of this stream: issued early so the loads overlap the transform
+        float2 *ola2 = reinterpret_cast<float2 *>(ola + (size_t) s * kFrame);
+        float2 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = ola2[lane + 32 * j];
+
         const float m255 = __shfl_sync(0xffffffffu, m[7], 31);   // lane 31 holds bins 248..255
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
@@ -166,33 +142,27 @@ backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const f
             const cpx yp = shfl_c(Y[bp], j == 0 ? src_a : src_b);
             const cpx E = {0.5f * (yk.x + yp.x), 0.5f * (yk.y - yp.y)};
             const cpx D = {0.5f * (yk.x - yp.x), 0.5f * (yk.y + yp.y)};
-            const float2 w = tw[8 * a + b];
-            const cpx O = cmulc(D, cpx{w.x, w.y});
+            const cpx O = cmulc(D, cpx{c.tp[b].x, c.tp[b].y});
             cpx zz = {E.x - O.y, E.y + O.x};
             if (j == 0 && lane == 0) zz = cpx{0.5f * (yk.x + yk.y), 0.5f * (yk.x - yk.y)};
             z[j] = zz;
         }
-        warp_ifft256_dit(z, tw, lane);
+        warp_ifft256_dit(z, c, lane);
 
         // z[j] = 256 (y[2p] + i y[2p+1]), p = lane + 32 j.  j < 4: first half -> output; j >= 4: second half -> new OLA tail.
-        float2 *ola2 = reinterpret_cast<float2 *>(ola + (size_t) s * kFrame);
         uint32_t *out32 = reinterpret_cast<uint32_t *>(v.out + (size_t) s * v.stride + (size_t) v.t * kFrame);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int p = lane + 32 * j;
-            const float2 w = win2[p], o = ola2[p];
-            const float v0 = o.x + w.x * (z[j].x * inv), v1 = o.y + w.y * (z[j].y * inv);
+            const float v0 = o[j].x + c.win[j].x * (z[j].x * inv), v1 = o[j].y + c.win[j].y * (z[j].y * inv);
             short i0, i1;   // round-to-nearest-even + saturate, the oracle's rintf + clamp
             asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i0) : "f"(v0));
             asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i1) : "f"(v1));
             out32[p] = (uint32_t) (uint16_t) i0 | ((uint32_t) (uint16_t) i1 << 16);
         }
 #pragma unroll
-        for (int j = 4; j < 8; ++j) {
-            const int p = lane + 32 * j;
-            const float2 w = win2[p];
-            ola2[p - 128] = make_float2(w.x * (z[j].x * inv), w.y * (z[j].y * inv));
-        }
+        for (int j = 4; j < 8; ++j)
+            ola2[lane + 32 * (j - 4)] = make_float2(c.win[j].x * (z[j].x * inv), c.win[j].y * (z[j].y * inv));
     }
 }
 
