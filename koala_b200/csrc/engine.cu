@@ -6,7 +6,8 @@
 //   h    [2][L][Bp][H] fp32  recurrent state, ping-pong by step parity (every unit tile reads all of h(t-1))
 //   hb   [2][L][Bp][H] bf16  the same state rounded to bf16 = GEMM operand of the tensor-core path
 // Scratch per step: feat [Bp][256] (fp32 | bf16), spec [Bp][512] fp32, e [Bp][H], mask [Bp][256] fp32.
-// Bp = B rounded up to 128 so that every GEMM tile is full; padding rows stay zero-input and are never copied out.
+// Bp = B rounded up to 256 (one CTA-pair tile) so that every GEMM tile is full; padding rows stay zero-input and are
+// never copied out.
 #include "engine.h"
 
 #include <math.h>
@@ -165,7 +166,7 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
     Engine *eng = new Engine();
     Impl *p = eng->p_ = new Impl();
     eng->n_ = num_streams;
-    eng->npad_ = (num_streams + 127) / 128 * 128;
+    eng->npad_ = (num_streams + 255) / 256 * 256;
     eng->device_ = device;
     eng->precision_ = precision;
     const size_t Bp = eng->npad_, H = model.hidden, L = model.layers;

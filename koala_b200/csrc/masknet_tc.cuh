@@ -2,17 +2,24 @@
 //
 // Middle stage of `pv_koala_process` (/root/reference/include/pv_koala.h:65-80); replaces the reference's per-stream
 // int8 x int16 dp2a mat-vec + LUT gate kernels by batched GEMMs over the stream dimension:
-// bf16 operands staged by TMA into 128B-swizzled shared memory, tcgen05.mma (cta_group::1, M = 128) accumulating fp32
-// in TMEM, gates / state update / activation fused into the epilogue that reads TMEM back with tcgen05.ld.
+// bf16 operands staged by TMA into 128B-swizzled shared memory, tcgen05.mma with cta_group::2 (a CTA pair = 256 streams
+// per tile, each SM loads its own 128 activation rows and HALF of the weight rows) accumulating fp32 in TMEM, gates /
+// state update / activation fused into the epilogue that reads TMEM back with tcgen05.ld.
 //
-// One persistent CTA per SM, 10 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
-// (two warps per TMEM lane quarter, splitting the columns; the first version had 4 epilogue warps and was epilogue-bound).  Two accumulator buffers of 256 TMEM columns let the epilogue of tile i overlap the MMAs
-// of tile i+1.
+// Why CTA pairs: the first version (cta_group::1, 128 x 192 tiles) was bound by the SM's L2 port -- 40 KB of operands per
+// 64-wide k-block against ~400 cycles of MMA (profiles/r01_step_summary.md).  Sharing the weight tile between the two
+// SMs of a pair cuts that to 28 KB.
 //
-// GRU tile = 128 streams x 64 hidden units.  TMEM columns: [r 0..63 | z 64..127 | n_x 128..191 | n_h 192..255].
-//   x-part (K = H):  one N=192 MMA per k-step   (packed W_ih rows r|z|n of the 64 units)        -> cols 0..191
-//   h-part (K = H):  N=128 MMA (W_hh rows r|z) accumulating on cols 0..127, N=64 MMA (W_hh rows n) -> cols 192..255
-// Linear tile = 128 streams x 256 outputs, one N=256 MMA per k-step.
+// One persistent CTA pair per 2 SMs, 10 warps per CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + (leader CTA only)
+// MMA issuer, warps 2-9 = epilogue (two warps per TMEM lane quarter, splitting the columns).  Two accumulator buffers of
+// 256 TMEM columns let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// GRU tile = 256 streams x 64 hidden units.  TMEM columns per buffer: [n_x 0..63 | r 64..127 | z 128..191 | n_h 192..255].
+//   x-part (K = H): one N=192 MMA per k-step, packed W_ih rows ordered n|r|z, D column base   0 -> n_x, r, z
+//   h-part (K = H): one N=192 MMA per k-step, packed W_hh rows ordered r|z|n, D column base  64 -> r, z (accumulated), n_h
+//   n_h has no zero-initialising MMA of its own (the accumulate flag is per instruction), so the epilogue clears those
+//   64 columns with tcgen05.st before it hands the buffer back.
+// Linear tile = 256 streams x 256 outputs, one N=256 MMA per k-step.
 #pragma once
 
 #include <cuda.h>
@@ -23,22 +30,28 @@
 
 namespace koala {
 
-constexpr int kTcBlockM = 128;
+constexpr int kTcBlockM = 128;                // rows per CTA; a pair covers 256
+constexpr int kTcPairM = 256;
 constexpr int kTcBlockK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
-constexpr int kTcStages = 4;
 constexpr int kTcABytes = kTcBlockM * 128;    // 16 KB
-constexpr int kTcBBytesMax = 256 * 128;       // 32 KB
-constexpr int kTcStageBytes = kTcABytes + kTcBBytesMax;
-constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*biases*/;
-constexpr int kTcThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kTcThreads = 320;               // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kTcAccCols = 256;
 constexpr int kGruUnits = 64;                 // hidden units per GRU tile
-constexpr int kGruRows = 3 * kGruUnits;       // packed weight rows per tile
+constexpr int kGruRows = 3 * kGruUnits;       // packed weight rows per tile (both CTAs together)
+constexpr int kTcTailBytes = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*biases*/;
 
 enum TcMode : int { kTcEnc = 0, kTcGru = 1, kTcDec = 2 };
 
+template <int MODE> struct TcCfg {
+    static constexpr bool kGru = MODE == kTcGru;
+    static constexpr int kBRowsHalf = kGru ? kGruRows / 2 : 128;        // weight rows each CTA of the pair loads
+    static constexpr int kStageBytes = kTcABytes + kBRowsHalf * 128;     // 28 KB | 32 KB
+    static constexpr int kStages = kGru ? 7 : 6;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kTcTailBytes;
+};
+
 struct TcArgs {
-    int num_m_tiles, num_n_tiles;
+    int num_m_tiles, num_n_tiles;   // m tiles of 256 streams
     int kb_per_part;            // K / 64 of one operand part (GRU has two parts: x then h)
     int H;
     const float *bias0;         // enc/dec bias | GRU b_ih
@@ -51,11 +64,30 @@ struct TcArgs {
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load whose completion bytes are signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *dst, int c0, int c1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
@@ -63,23 +95,27 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// arrives (once the MMAs issued so far have completed) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t) 3)
+                 : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem, 256 rows over the pair] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -94,6 +130,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// clears 16 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+        "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows at 128 B pitch, 8-row groups at 1024 B (SBO), version 1 (sm_100), layout 2
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -117,22 +162,26 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float *f) {
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1, const TcArgs args) {
-    constexpr bool kGru = MODE == kTcGru;
-    constexpr int kBRows = kGru ? kGruRows : 256;
-    constexpr uint32_t kStageTx = kTcABytes + kBRows * 128;
+    using Cfg = TcCfg<MODE>;
+    constexpr bool kGru = Cfg::kGru;
+    constexpr int kStages = Cfg::kStages, kStageBytes = Cfg::kStageBytes, kBRowsHalf = Cfg::kBRowsHalf;
+    constexpr uint32_t kPairTx = 2u * kStageBytes;   // bytes both CTAs land per stage, all signalled on the leader's barrier
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTcStages * kTcStageBytes);
-    uint64_t *full_bar = bars, *empty_bar = bars + kTcStages;
-    uint64_t *tmem_full = bars + 2 * kTcStages, *tmem_empty = bars + 2 * kTcStages + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTcStages + 4);
-    float *s_bias = reinterpret_cast<float *>(smem + kTcStages * kTcStageBytes + 256);   // [2 accumulator buffers][256]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint64_t *full_bar = bars, *empty_bar = bars + kStages;
+    uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    float *s_bias = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256);   // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs), 1 = peer
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a0);
         prefetch_tmap(&map_b0);
@@ -140,19 +189,19 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             prefetch_tmap(&map_a1);
             prefetch_tmap(&map_b1);
         }
-        for (int s = 0; s < kTcStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);     // leader's copy is the one in use: 1 arrive.expect_tx + 2 CTAs' TMA bytes
+            mbar_init(&empty_bar[s], 1);    // one multicast tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], 256);
+            mbar_init(&tmem_full[b], 1);    // one multicast tcgen05.commit
+            mbar_init(&tmem_empty[b], 512); // leader's copy: 256 epilogue threads of each CTA
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * kTcAccCols);
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * kTcAccCols);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -160,74 +209,85 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const int num_kb = (kGru ? 2 : 1) * args.kb_per_part;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
+        // ===================================================== TMA producer (both CTAs: own A rows, own half of B rows)
         if (lane == 0) {
             int stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 const int m = tile / args.num_n_tiles, n = tile % args.num_n_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], kStageTx);
-                    uint8_t *sa = smem + stage * kTcStageBytes, *sb = sa + kTcABytes;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], kPairTx);
+                    const uint32_t full_leader = map_to_cta(&full_bar[stage], 0);
+                    uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kTcABytes;
                     const bool second = kGru && kb >= args.kb_per_part;
                     const int kc = (second ? kb - args.kb_per_part : kb) * kTcBlockK;
-                    tma_load_2d(second ? &map_a1 : &map_a0, &full_bar[stage], sa, kc, m * kTcBlockM);
-                    tma_load_2d(second ? &map_b1 : &map_b0, &full_bar[stage], sb, kc, n * kBRows);
-                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                    tma_load_2d_pair(second ? &map_a1 : &map_a0, full_leader, sa, kc, m * kTcPairM + (int) rank * kTcBlockM);
+                    tma_load_2d_pair(second ? &map_b1 : &map_b0, full_leader, sb, kc, n * 2 * kBRowsHalf + (int) rank * kBRowsHalf);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================== MMA issuer (one thread of the leader CTA drives both SMs)
+        if (lane == 0 && rank == 0) {
             int stage = 0, phase = 0, it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
                 const int ab = it & 1, aphase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[ab], aphase ^ 1);
+                mbar_wait(&tmem_empty[ab], aphase);      // both CTAs' epilogues have released (and cleared) this buffer
                 tc_fence_after();
                 const uint32_t d = tmem_base + ab * kTcAccCols;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * kTcStageBytes), sb = sa + kTcABytes;
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes), sb = sa + kTcABytes;
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sb);
 #pragma unroll
                     for (int k = 0; k < kTcBlockK / 16; ++k) {
                         const uint64_t ad = adesc + 2 * k, bd = bdesc + 2 * k;   // +32 B per 16-element k-step
-                        if (!kGru) {
-                            umma_bf16(d, ad, bd, make_idesc(128, 256), (kb | k) != 0);
-                        } else if (kb < args.kb_per_part) {
-                            umma_bf16(d, ad, bd, make_idesc(128, 192), (kb | k) != 0);
-                        } else {
-                            umma_bf16(d, ad, bd, make_idesc(128, 128), 1u);
-                            umma_bf16(d + 192, ad, bd + ((128 * 128) >> 4), make_idesc(128, 64),
-                                      (kb != args.kb_per_part || k != 0));
-                        }
+                        if (!kGru) umma_bf16_pair(d, ad, bd, make_idesc(256, 256), (kb | k) != 0);
+                        else if (kb < args.kb_per_part) umma_bf16_pair(d, ad, bd, make_idesc(256, kGruRows), (kb | k) != 0);
+                        else umma_bf16_pair(d + kGruUnits, ad, bd, make_idesc(256, kGruRows), 1u);
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                    umma_commit_pair(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[ab]);
+                umma_commit_pair(&tmem_full[ab]);
             }
         }
     } else {
         // ===================================================== epilogue: warps 2..9; TMEM lane quarter = warp % 4, the two
         // warps of a quarter split the columns (GRU: 32 of the 64 units each; linear: 128 of the 256 outputs each)
         const int quarter = warp & 3, half = (warp - 2) >> 2, te = threadIdx.x - 64;
+        const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
+        uint32_t empty_leader[2] = {map_to_cta(&tmem_empty[0], 0), map_to_cta(&tmem_empty[1], 0)};
+        // hand both buffers to the MMA issuer for the first time (GRU: with the n_h columns cleared)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            if (kGru) {
+                tmem_zero16(lane_base + b * kTcAccCols + 192 + half * 32);
+                tmem_zero16(lane_base + b * kTcAccCols + 192 + half * 32 + 16);
+            }
+        }
+        if (kGru) tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_cluster(empty_leader[0]);
+        mbar_arrive_cluster(empty_leader[1]);
+
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
             const int m = tile / args.num_n_tiles, n = tile % args.num_n_tiles;
             const int ab = it & 1, aphase = (it >> 1) & 1;
-            const size_t row = (size_t) m * kTcBlockM + quarter * 32 + lane;
+            const size_t row = (size_t) m * kTcPairM + rank * kTcBlockM + quarter * 32 + lane;
             float *sb = s_bias + ab * 256;
             float hp[32];
             if (kGru) {
-                // biases of this tile -> smem ([r | z | n_x | n_h] x 64), previous state of my 32 units -> registers;
-                // both are independent of the MMAs, so they are fetched before waiting for the accumulator
+                // biases of this tile -> smem ([n_x | r | z | n_h] x 64, same order as the TMEM columns), previous state
+                // of my 32 units -> registers; both are independent of the MMAs and fetched before the accumulator wait
                 const int H = args.H, g = te >> 6, u = n * kGruUnits + (te & 63);
-                sb[te] = g == 0 ? __ldg(args.bias0 + u) + __ldg(args.bias1 + u)
-                       : g == 1 ? __ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u)
-                       : g == 2 ? __ldg(args.bias0 + 2 * H + u) : __ldg(args.bias1 + 2 * H + u);
+                sb[te] = g == 0 ? __ldg(args.bias0 + 2 * H + u)
+                       : g == 1 ? __ldg(args.bias0 + u) + __ldg(args.bias1 + u)
+                       : g == 2 ? __ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u)
+                                : __ldg(args.bias1 + 2 * H + u);
                 const float4 *hp4 = reinterpret_cast<const float4 *>(args.h_prev + row * H + n * kGruUnits + half * 32);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -240,27 +300,28 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             asm volatile("bar.sync 1, 256;" ::: "memory");   // the 256 epilogue threads only
             mbar_wait(&tmem_full[ab], aphase);
             tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t) (quarter * 32) << 16) + ab * kTcAccCols;
+            const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (kGru) {
                 const int H = args.H;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int cu = half * 32 + c * 16;           // first unit of this chunk inside the tile
-                    float ar[16], az[16], anx[16], anh[16], hn[16];
-                    tmem_ld16(t0 + 0 + cu, ar);
-                    tmem_ld16(t0 + 64 + cu, az);
-                    tmem_ld16(t0 + 128 + cu, anx);
+                    float anx[16], ar[16], az[16], anh[16], hn[16];
+                    tmem_ld16(t0 + 0 + cu, anx);
+                    tmem_ld16(t0 + 64 + cu, ar);
+                    tmem_ld16(t0 + 128 + cu, az);
                     tmem_ld16(t0 + 192 + cu, anh);
                     tmem_ld_wait();
+                    tmem_zero16(t0 + 192 + cu);                  // n_h columns must be zero when the buffer is reused
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         // r = 1/(1+er), z = 1/(1+ez) with one shared reciprocal: 5 MUFU ops per unit instead of 6
-                        const float er = __expf(fminf(-(ar[i] + sb[cu + i]), 30.0f));
-                        const float ez = __expf(fminf(-(az[i] + sb[64 + cu + i]), 30.0f));
+                        const float er = __expf(fminf(-(ar[i] + sb[64 + cu + i]), 30.0f));
+                        const float ez = __expf(fminf(-(az[i] + sb[128 + cu + i]), 30.0f));
                         const float pr = 1.0f + er, pz = 1.0f + ez;
                         const float ip = __fdividef(1.0f, pr * pz);
                         const float rg = pz * ip, zg = pr * ip;
-                        const float ng = tanh_f(anx[i] + sb[128 + cu + i] + rg * (anh[i] + sb[192 + cu + i]));
+                        const float ng = tanh_f(anx[i] + sb[cu + i] + rg * (anh[i] + sb[192 + cu + i]));
                         hn[i] = (1.0f - zg) * ng + zg * hp[c * 16 + i];
                     }
                     const size_t off = row * H + n * kGruUnits + cu;
@@ -271,6 +332,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                     hb4[0] = pack_bf16x8(hn);
                     hb4[1] = pack_bf16x8(hn + 8);
                 }
+                tmem_st_wait();
             } else {
                 const int N = args.num_n_tiles * 256;
 #pragma unroll 2
@@ -297,22 +359,25 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[ab]);
+            mbar_arrive_cluster(empty_leader[ab]);
         }
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();      // the peer's smem / TMEM are read and written by the leader's MMAs: leave together
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * kTcAccCols);
+        tmem_dealloc_pair(tmem_base, 2 * kTcAccCols);
     }
 }
 
-// packed[(n * 3 + g) * 64 + u][k] = W[g * H + n * 64 + u][k]: the three gate rows of one unit tile become contiguous
-__global__ void pack_gru_weights_kernel(const __nv_bfloat16 *__restrict__ W, __nv_bfloat16 *__restrict__ packed, int H) {
+// Packs the three gate rows of each 64-unit tile contiguously: packed[(n * 3 + slot) * 64 + u][k] = W[gate * H + n * 64 + u][k]
+// with gate = order[slot] (PyTorch gate numbering r=0, z=1, n=2): W_ih uses n|r|z, W_hh uses r|z|n (see file header).
+__global__ void pack_gru_weights_kernel(const __nv_bfloat16 *__restrict__ W, __nv_bfloat16 *__restrict__ packed, int H, int g0,
+                                        int g1, int g2) {
     const int prow = blockIdx.x;
-    const int n = prow / kGruRows, g = (prow % kGruRows) / kGruUnits, u = prow % kGruUnits;
-    const uint4 *src = reinterpret_cast<const uint4 *>(W + (size_t) (g * H + n * kGruUnits + u) * H);
+    const int n = prow / kGruRows, slot = (prow % kGruRows) / kGruUnits, u = prow % kGruUnits;
+    const int gate = slot == 0 ? g0 : slot == 1 ? g1 : g2;
+    const uint4 *src = reinterpret_cast<const uint4 *>(W + (size_t) (gate * H + n * kGruUnits + u) * H);
     uint4 *dst = reinterpret_cast<uint4 *>(packed + (size_t) prow * H);
     for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
 }
@@ -359,8 +424,8 @@ static void tc_plan_destroy(TcPlan *p) {
 }
 
 static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
-    if (m.H % 256 != 0 || m.Bp % kTcBlockM != 0) {
-        *why = "hidden size must be a multiple of 256 for the tensor-core path";
+    if (m.H % 256 != 0 || m.Bp % kTcPairM != 0) {
+        *why = "hidden size and padded stream count must be multiples of 256 for the tensor-core path";
         return false;
     }
     void *fnp = nullptr;
@@ -382,8 +447,8 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
         ok = cudaMalloc((void **) &p->wih_p[l], 3 * H * H * 2) == cudaSuccess &&
              cudaMalloc((void **) &p->whh_p[l], 3 * H * H * 2) == cudaSuccess;
         if (!ok) break;
-        pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.wih[l], p->wih_p[l], (int) H);
-        pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.whh[l], p->whh_p[l], (int) H);
+        pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.wih[l], p->wih_p[l], (int) H, 2, 0, 1);   // n | r | z
+        pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.whh[l], p->whh_p[l], (int) H, 0, 1, 2);   // r | z | n
     }
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
@@ -395,20 +460,20 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
     ok = ok && encode_2d(fn, &p->a_e, m.e, Bp, H, kTcBlockM);
     for (int par = 0; par < 2; par++)
         for (int l = 0; l < m.L; l++) ok = ok && encode_2d(fn, &p->a_hb[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, kTcBlockM);
-    ok = ok && encode_2d(fn, &p->b_enc, m.enc_w, H, kBins, 256);
-    ok = ok && encode_2d(fn, &p->b_dec, m.dec_w, kBins, H, 256);
+    ok = ok && encode_2d(fn, &p->b_enc, m.enc_w, H, kBins, TcCfg<kTcEnc>::kBRowsHalf);
+    ok = ok && encode_2d(fn, &p->b_dec, m.dec_w, kBins, H, TcCfg<kTcDec>::kBRowsHalf);
     for (int l = 0; l < m.L; l++) {
-        ok = ok && encode_2d(fn, &p->b_ih[l], p->wih_p[l], 3 * H, H, kGruRows);
-        ok = ok && encode_2d(fn, &p->b_hh[l], p->whh_p[l], 3 * H, H, kGruRows);
+        ok = ok && encode_2d(fn, &p->b_ih[l], p->wih_p[l], 3 * H, H, TcCfg<kTcGru>::kBRowsHalf);
+        ok = ok && encode_2d(fn, &p->b_hh[l], p->whh_p[l], 3 * H, H, TcCfg<kTcGru>::kBRowsHalf);
     }
     if (!ok) {
         *why = "cuTensorMapEncodeTiled failed";
         tc_plan_destroy(p);
         return false;
     }
-    ok = cudaFuncSetAttribute(tc_masknet_kernel<kTcEnc>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
-         cudaFuncSetAttribute(tc_masknet_kernel<kTcGru>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
-         cudaFuncSetAttribute(tc_masknet_kernel<kTcDec>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
+    ok = cudaFuncSetAttribute(tc_masknet_kernel<kTcEnc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<kTcEnc>::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(tc_masknet_kernel<kTcGru>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<kTcGru>::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(tc_masknet_kernel<kTcDec>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<kTcDec>::kSmemBytes) == cudaSuccess;
     if (!ok) {
         *why = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
         tc_plan_destroy(p);
@@ -421,15 +486,16 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
 // one mask-estimator step: hb[cur]/h[cur] hold state t-1, results go to hb[cur^1]/h[cur^1]; returns kernels launched
 static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *prof) {
     const TcModel &m = p->m;
-    const int nxt = cur ^ 1, H = m.H, mt = m.Bp / kTcBlockM;
+    const int nxt = cur ^ 1, H = m.H, mt = m.Bp / kTcPairM;
     const size_t LBH = (size_t) m.Bp * H;
-    auto grid = [&](int tiles) { return tiles < p->num_sms ? tiles : p->num_sms; };
+    const int max_pairs = p->num_sms / 2;
+    auto grid = [&](int tiles) { return 2 * (tiles < max_pairs ? tiles : max_pairs); };   // CTAs: one pair per tile slot
     {
         TcArgs a{};
         a.num_m_tiles = mt; a.num_n_tiles = H / 256; a.kb_per_part = kBins / kTcBlockK; a.H = H;
         a.bias0 = m.enc_b; a.out_bf16 = m.e;
         if (prof) prof->begin(kKernEnc, st);
-        tc_masknet_kernel<kTcEnc><<<grid(mt * a.num_n_tiles), kTcThreads, kTcSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, a);
+        tc_masknet_kernel<kTcEnc><<<grid(mt * a.num_n_tiles), kTcThreads, TcCfg<kTcEnc>::kSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, a);
         if (prof) prof->end(st);
     }
     for (int l = 0; l < m.L; l++) {
@@ -439,7 +505,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.h_prev = m.h[cur] + l * LBH; a.h_next = m.h[nxt] + l * LBH; a.out_bf16 = m.hb[nxt] + l * LBH;
         const CUtensorMap &ax = l == 0 ? p->a_e : p->a_hb[nxt][l - 1];
         if (prof) prof->begin(kKernGru, st);
-        tc_masknet_kernel<kTcGru><<<grid(mt * a.num_n_tiles), kTcThreads, kTcSmemBytes, st>>>(ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], a);
+        tc_masknet_kernel<kTcGru><<<grid(mt * a.num_n_tiles), kTcThreads, TcCfg<kTcGru>::kSmemBytes, st>>>(ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], a);
         if (prof) prof->end(st);
     }
     {
@@ -447,7 +513,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.num_m_tiles = mt; a.num_n_tiles = kBins / 256; a.kb_per_part = H / kTcBlockK; a.H = H;
         a.bias0 = m.dec_b; a.out_f32 = m.mask;
         if (prof) prof->begin(kKernDec, st);
-        tc_masknet_kernel<kTcDec><<<grid(mt * a.num_n_tiles), kTcThreads, kTcSmemBytes, st>>>(p->a_hb[nxt][m.L - 1], p->a_hb[nxt][m.L - 1], p->b_dec, p->b_dec, a);
+        tc_masknet_kernel<kTcDec><<<grid(mt * a.num_n_tiles), kTcThreads, TcCfg<kTcDec>::kSmemBytes, st>>>(p->a_hb[nxt][m.L - 1], p->a_hb[nxt][m.L - 1], p->b_dec, p->b_dec, a);
         if (prof) prof->end(st);
     }
     return 2 + m.L;
