@@ -435,6 +435,7 @@ Status Engine::debug_read(const char *name, void *dst, size_t bytes, std::vector
     else if (nm == "e") { src = p->e; avail = B * H * esz; }
     else if (nm == "ola") { src = p->ola; avail = B * kFrame * 4; }
     else if (nm == "tail") { src = p->tail; avail = B * kFrame * 2; }
+    else if (nm == "trace" && p->tc && p->tc->trace) { src = p->tc->trace; avail = 1024 * sizeof(long long); }
     else if (nm.size() == 2 && nm[0] == 'h' && nm[1] >= '0' && nm[1] < '0' + p->L) {
         src = p->h[p->parity] + (size_t) (nm[1] - '0') * Bp * H;   // h(t) of the last finished step
         avail = B * H * 4;

@@ -23,6 +23,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -34,7 +35,7 @@ constexpr int kTcBlockM = 128;                // rows per CTA; a pair covers 256
 constexpr int kTcPairM = 256;
 constexpr int kTcBlockK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kTcABytes = kTcBlockM * 128;    // 16 KB
-constexpr int kTcThreads = 320;               // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kTcThreads = 352;               // TMA warp (A) + MMA warp + 8 epilogue warps + TMA warp (B)
 constexpr int kTcAccCols = 256;
 constexpr int kGruUnits = 64;                 // hidden units per GRU tile
 constexpr int kGruRows = 3 * kGruUnits;       // packed weight rows per tile (both CTAs together)
@@ -42,10 +43,18 @@ constexpr int kTcTailBytes = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bi
 
 enum TcMode : int { kTcEnc = 0, kTcGru = 1, kTcDec = 2 };
 
+// A cluster is a PM x PN grid of CTA pairs: pair (qm, qn) works on M-tile cm * PM + qm and N-tile cn * PN + qn of the
+// cluster tile (cm, cn).  The PN pairs of a row need the same activation rows and the PM pairs of a column the same
+// weight rows, so every CTA fetches only 1/PN of its A block and 1/PM of its B block and TMA-multicasts the piece to
+// the CTAs that share it: L2 -> SM traffic per pair-tile drops from (A + B) to (A / PN + B / PM).
 template <int MODE> struct TcCfg {
     static constexpr bool kGru = MODE == kTcGru;
-    static constexpr int kBRowsHalf = kGru ? kGruRows / 2 : 128;        // weight rows each CTA of the pair loads
-    static constexpr int kStageBytes = kTcABytes + kBRowsHalf * 128;     // 28 KB | 32 KB
+    static constexpr int kPM = 1, kPN = kGru ? 2 : 1;   // GRU: 4-CTA clusters, activations multicast across 2 unit tiles
+    static constexpr int kPairs = kPM * kPN, kCluster = 2 * kPairs;
+    static constexpr int kBRowsHalf = kGru ? kGruRows / 2 : 128;        // weight rows each CTA of a pair holds
+    static constexpr int kARowsPiece = kTcBlockM / kPN;                  // rows of A this CTA fetches (and multicasts)
+    static constexpr int kBRowsPiece = kBRowsHalf / kPM;                 // rows of B this CTA fetches (and multicasts)
+    static constexpr int kStageBytes = kTcABytes + kBRowsHalf * 128;     // 28 KB | 32 KB landing per CTA per stage
     static constexpr int kStages = kGru ? 7 : 6;
     static constexpr int kSmemBytes = kStages * kStageBytes + kTcTailBytes;
 };
@@ -60,6 +69,7 @@ struct TcArgs {
     float *h_next;              // GRU fp32 state out [Bp][H]
     __nv_bfloat16 *out_bf16;    // enc: e [Bp][H]; GRU: bf16 copy of h_next
     float *out_f32;             // dec: mask [Bp][256]
+    long long *trace;           // optional clock64() timeline of CTAs 0 and 1 (KOALA_TC_TRACE=1), else nullptr
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -68,6 +78,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
+}
+// one lane of a converged warp; keeps the surrounding code warp-uniform so that descriptors stay in uniform registers
+// (issuing from inside `if (lane == 0)` made ptxas wrap every tcgen05.mma / TMA in an R2UR waterfall loop, ~140 cycles each)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -80,7 +97,9 @@ __device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // relaxed: the only thing this arrival publishes is "my TMEM reads/writes are done", which tcgen05.fence orders;
+    // a release at cluster scope compiles to MEMBAR.ALL.GPU and stalls on every outstanding global store
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tile load whose completion bytes are signalled on a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *dst, int c0, int c1) {
@@ -88,6 +107,16 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(dst)),
         "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+// same, multicast: the tile lands at the same smem offset in every CTA of `mask`, and each destination's completion bytes
+// are signalled on the barrier at this offset in the leader of the destination's pair
+__device__ __forceinline__ void tma_load_2d_pair_mc(const CUtensorMap *map, uint32_t bar_cluster_addr, void *dst, int c0, int c1,
+                                                    uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+        "%4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
@@ -103,11 +132,11 @@ __device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t nco
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// arrives (once the MMAs issued so far have completed) on the barrier at this smem offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+// arrives (once the MMAs issued so far have completed) on the barrier at this smem offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
-                 "h"((uint16_t) 3)
+                 "h"(mask)
                  : "memory");
 }
 // D[tmem, 256 rows over the pair] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T, bf16 x bf16 -> fp32
@@ -162,13 +191,14 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float *f) {
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+__global__ void __cluster_dims__(TcCfg<MODE>::kCluster, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1, const TcArgs args) {
     using Cfg = TcCfg<MODE>;
     constexpr bool kGru = Cfg::kGru;
     constexpr int kStages = Cfg::kStages, kStageBytes = Cfg::kStageBytes, kBRowsHalf = Cfg::kBRowsHalf;
-    constexpr uint32_t kPairTx = 2u * kStageBytes;   // bytes both CTAs land per stage, all signalled on the leader's barrier
+    constexpr int kPM = Cfg::kPM, kPN = Cfg::kPN, kCluster = Cfg::kCluster;
+    constexpr uint32_t kPairTx = 2u * kStageBytes;   // bytes landing in both CTAs of a pair per stage, signalled on its leader
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
@@ -179,8 +209,15 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     float *s_bias = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256);   // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs), 1 = peer
-    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const uint32_t crank = cluster_ctarank();      // rank in the cluster = 2 * pair + position in pair
+    const uint32_t rank = crank & 1;               // 0 = pair leader (issues the MMAs), 1 = peer
+    const uint32_t leader = crank & ~1u;           // cluster rank of my pair's leader
+    const int q = (int) (crank >> 1), qm = q % kPM, qn = q / kPM;
+    const uint16_t pair_mask = (uint16_t) (3u << leader), all_mask = (uint16_t) ((1u << kCluster) - 1);
+    long long *trace = (args.trace != nullptr && blockIdx.x < 2) ? args.trace + blockIdx.x * 512 : nullptr;
+#define KTRACE(slot) do { if (trace && (slot) < 512) trace[(slot)] = clock64(); } while (0)
+    if (threadIdx.x == 0) KTRACE(500);
+    const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a0);
@@ -191,7 +228,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);     // leader's copy is the one in use: 1 arrive.expect_tx + 2 CTAs' TMA bytes
-            mbar_init(&empty_bar[s], 1);    // one multicast tcgen05.commit
+            mbar_init(&empty_bar[s], Cfg::kPairs);   // one multicast tcgen05.commit from every pair leader of the cluster
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);    // one multicast tcgen05.commit
@@ -204,43 +241,75 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) KTRACE(501);
 
-    const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+    // cluster tiles: (num_m_tiles / PM) x (num_n_tiles / PN); every pair of the cluster walks the same sequence
+    const int ctiles_n = args.num_n_tiles / kPN;
+    const int num_tiles = (args.num_m_tiles / kPM) * ctiles_n;
     const int num_kb = (kGru ? 2 : 1) * args.kb_per_part;
 
-    if (warp == 0) {
-        // ===================================================== TMA producer (both CTAs: own A rows, own half of B rows)
-        if (lane == 0) {
-            int stage = 0, phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                const int m = tile / args.num_n_tiles, n = tile % args.num_n_tiles;
+    if (warp == 0 || warp == 10) {
+        // ===================================================== TMA producers (both CTAs of every pair).  One thread can
+        // issue a tensor load only every ~210 cycles whatever its size (tools/micro/tma_rate.cu), so the activation (A)
+        // and weight (B) tiles of a k-block are issued by two different warps: warp 0 loads A, warp 10 loads B.
+        {
+            const bool is_a = warp == 0;
+            int stage = 0, phase = 0, pit = 0;
+            // multicast destinations: A goes to the CTAs with my (qm, position), B to those with my (qn, position)
+            uint16_t mask_a = 0, mask_b = 0;
+#pragma unroll
+            for (int j = 0; j < kPN; ++j) mask_a |= (uint16_t) (1u << (2 * (qm + kPM * j) + rank));
+#pragma unroll
+            for (int j = 0; j < kPM; ++j) mask_b |= (uint16_t) (1u << (2 * (j + kPM * qn) + rank));
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++pit) {
+                const int m = (tile / ctiles_n) * kPM + qm, n = (tile % ctiles_n) * kPN + qn;
+                if (is_a && lane == 0) KTRACE(pit * 48 + 0);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (rank == 0) mbar_expect_tx(&full_bar[stage], kPairTx);
-                    const uint32_t full_leader = map_to_cta(&full_bar[stage], 0);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);     // slot free in every CTA of the cluster
+                    if (is_a && lane == 0) KTRACE(pit * 48 + 16 + kb);
+                    const bool elected = elect_one();
+                    if (elected && is_a && rank == 0) mbar_expect_tx(&full_bar[stage], kPairTx);
+                    const uint32_t full_leader = map_to_cta(&full_bar[stage], leader);
                     uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kTcABytes;
                     const bool second = kGru && kb >= args.kb_per_part;
                     const int kc = (second ? kb - args.kb_per_part : kb) * kTcBlockK;
-                    tma_load_2d_pair(second ? &map_a1 : &map_a0, full_leader, sa, kc, m * kTcPairM + (int) rank * kTcBlockM);
-                    tma_load_2d_pair(second ? &map_b1 : &map_b0, full_leader, sb, kc, n * 2 * kBRowsHalf + (int) rank * kBRowsHalf);
+                    if (!elected) {
+                    } else if (is_a) {
+                        const CUtensorMap *ma = second ? &map_a1 : &map_a0;
+                        const int arow = m * kTcPairM + (int) rank * kTcBlockM + qn * Cfg::kARowsPiece;
+                        if (kPN > 1) tma_load_2d_pair_mc(ma, full_leader, sa + qn * Cfg::kARowsPiece * 128, kc, arow, mask_a);
+                        else tma_load_2d_pair(ma, full_leader, sa, kc, arow);
+                    } else {
+                        const CUtensorMap *mb = second ? &map_b1 : &map_b0;
+                        const int brow = n * 2 * kBRowsHalf + (int) rank * kBRowsHalf + qm * Cfg::kBRowsPiece;
+                        if (kPM > 1) tma_load_2d_pair_mc(mb, full_leader, sb + qm * Cfg::kBRowsPiece * 128, kc, brow, mask_b);
+                        else tma_load_2d_pair(mb, full_leader, sb, kc, brow);
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                if (is_a && lane == 0) KTRACE(pit * 48 + 1);
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer (one thread of the leader CTA drives both SMs)
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             int stage = 0, phase = 0, it = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
                 const int ab = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[ab], aphase);      // both CTAs' epilogues have released (and cleared) this buffer
                 tc_fence_after();
+                if (lane == 0) KTRACE(it * 48 + 2);
                 const uint32_t d = tmem_base + ab * kTcAccCols;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    if (it == 1 && lane == 0) KTRACE(256 + kb * 4 + 0);
                     mbar_wait(&full_bar[stage], phase);
+                    if (it == 1 && lane == 0) KTRACE(256 + kb * 4 + 1);
                     tc_fence_after();
+                    if (lane == 0) KTRACE(it * 48 + 32 + kb);
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes), sb = sa + kTcABytes;
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sb);
+                    if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kTcBlockK / 16; ++k) {
                         const uint64_t ad = adesc + 2 * k, bd = bdesc + 2 * k;   // +32 B per 16-element k-step
@@ -248,18 +317,23 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                         else if (kb < args.kb_per_part) umma_bf16_pair(d, ad, bd, make_idesc(256, kGruRows), (kb | k) != 0);
                         else umma_bf16_pair(d + kGruUnits, ad, bd, make_idesc(256, kGruRows), 1u);
                     }
-                    umma_commit_pair(&empty_bar[stage]);
+                    umma_commit_pair(&empty_bar[stage], all_mask);   // partners multicast into my slots, so everyone must know
+                    }
+                    __syncwarp();
+                    if (it == 1 && lane == 0) KTRACE(256 + kb * 4 + 3);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_pair(&tmem_full[ab]);
+                if (elect_one()) umma_commit_pair(&tmem_full[ab], pair_mask);
+                __syncwarp();
+                if (lane == 0) KTRACE(it * 48 + 3);
             }
         }
-    } else {
+    } else if (warp < 10) {
         // ===================================================== epilogue: warps 2..9; TMEM lane quarter = warp % 4, the two
         // warps of a quarter split the columns (GRU: 32 of the 64 units each; linear: 128 of the 256 outputs each)
-        const int quarter = warp & 3, half = (warp - 2) >> 2, te = threadIdx.x - 64;
+        const int quarter = warp & 3, half = (warp - 2) >> 2, te = threadIdx.x - 64;   // warps 2..9 only
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
-        uint32_t empty_leader[2] = {map_to_cta(&tmem_empty[0], 0), map_to_cta(&tmem_empty[1], 0)};
+        uint32_t empty_leader[2] = {map_to_cta(&tmem_empty[0], leader), map_to_cta(&tmem_empty[1], leader)};
         // hand both buffers to the MMA issuer for the first time (GRU: with the n_h columns cleared)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
@@ -274,8 +348,8 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         mbar_arrive_cluster(empty_leader[1]);
 
         int it = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-            const int m = tile / args.num_n_tiles, n = tile % args.num_n_tiles;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            const int m = (tile / ctiles_n) * kPM + qm, n = (tile % ctiles_n) * kPN + qn;
             const int ab = it & 1, aphase = (it >> 1) & 1;
             const size_t row = (size_t) m * kTcPairM + rank * kTcBlockM + quarter * 32 + lane;
             float *sb = s_bias + ab * 256;
@@ -298,8 +372,10 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 sb[te] = __ldg(args.bias0 + n * 256 + te);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");   // the 256 epilogue threads only
+            if (te == 0) KTRACE(it * 48 + 4);
             mbar_wait(&tmem_full[ab], aphase);
             tc_fence_after();
+            if (te == 0) KTRACE(it * 48 + 5);
             const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (kGru) {
                 const int H = args.H;
@@ -359,15 +435,20 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 }
             }
             tc_fence_before();
+            if (te == 0) KTRACE(it * 48 + 6);
             mbar_arrive_cluster(empty_leader[ab]);
+            if (te == 0) KTRACE(it * 48 + 7);
         }
     }
+    if (threadIdx.x == 0) KTRACE(502);
     tc_fence_before();
     cluster_sync_all();      // the peer's smem / TMEM are read and written by the leader's MMAs: leave together
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, 2 * kTcAccCols);
     }
+    if (threadIdx.x == 0) KTRACE(503);
+#undef KTRACE
 }
 
 // Packs the three gate rows of each 64-unit tile contiguously: packed[(n * 3 + slot) * 64 + u][k] = W[gate * H + n * 64 + u][k]
@@ -395,9 +476,12 @@ struct TcModel {
 struct TcPlan {
     TcModel m;
     int num_sms = 0;
+    long long *trace = nullptr;   // 2 x 512 clock64 slots, filled by the first GRU layer when KOALA_TC_TRACE=1
     __nv_bfloat16 *wih_p[kMaxLayers] = {}, *whh_p[kMaxLayers] = {};
-    CUtensorMap a_feat, a_e, a_hb[2][kMaxLayers];      // activation operands [Bp][K], box 64 x 128
+    CUtensorMap a_feat, a_hb_dec[2];                    // linear kernels: activation operands [Bp][K], box 64 x 128
+    CUtensorMap a_e, a_hb[2][kMaxLayers];               // GRU kernel: box 64 x (128 / PN)
     CUtensorMap b_enc, b_dec, b_ih[kMaxLayers], b_hh[kMaxLayers];
+    int max_clusters[3] = {0, 0, 0};                    // co-resident clusters per kernel (cudaOccupancyMaxActiveClusters)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -420,12 +504,13 @@ static void tc_plan_destroy(TcPlan *p) {
         if (p->wih_p[l]) cudaFree(p->wih_p[l]);
         if (p->whh_p[l]) cudaFree(p->whh_p[l]);
     }
+    if (p->trace) cudaFree(p->trace);
     delete p;
 }
 
 static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
-    if (m.H % 256 != 0 || m.Bp % kTcPairM != 0) {
-        *why = "hidden size and padded stream count must be multiples of 256 for the tensor-core path";
+    if (m.H % 256 != 0 || m.Bp % (kTcPairM * TcCfg<kTcGru>::kPM) != 0) {
+        *why = "hidden size must be a multiple of 256 and the padded stream count a multiple of the cluster tile for the tensor-core path";
         return false;
     }
     void *fnp = nullptr;
@@ -457,14 +542,17 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
         return false;
     }
     ok = ok && encode_2d(fn, &p->a_feat, m.feat, Bp, kBins, kTcBlockM);
-    ok = ok && encode_2d(fn, &p->a_e, m.e, Bp, H, kTcBlockM);
-    for (int par = 0; par < 2; par++)
-        for (int l = 0; l < m.L; l++) ok = ok && encode_2d(fn, &p->a_hb[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, kTcBlockM);
+    ok = ok && encode_2d(fn, &p->a_e, m.e, Bp, H, TcCfg<kTcGru>::kARowsPiece);
+    for (int par = 0; par < 2; par++) {
+        for (int l = 0; l < m.L; l++)
+            ok = ok && encode_2d(fn, &p->a_hb[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, TcCfg<kTcGru>::kARowsPiece);
+        ok = ok && encode_2d(fn, &p->a_hb_dec[par], m.hb[par] + (size_t) (m.L - 1) * Bp * H, Bp, H, kTcBlockM);
+    }
     ok = ok && encode_2d(fn, &p->b_enc, m.enc_w, H, kBins, TcCfg<kTcEnc>::kBRowsHalf);
     ok = ok && encode_2d(fn, &p->b_dec, m.dec_w, kBins, H, TcCfg<kTcDec>::kBRowsHalf);
     for (int l = 0; l < m.L; l++) {
-        ok = ok && encode_2d(fn, &p->b_ih[l], p->wih_p[l], 3 * H, H, TcCfg<kTcGru>::kBRowsHalf);
-        ok = ok && encode_2d(fn, &p->b_hh[l], p->whh_p[l], 3 * H, H, TcCfg<kTcGru>::kBRowsHalf);
+        ok = ok && encode_2d(fn, &p->b_ih[l], p->wih_p[l], 3 * H, H, TcCfg<kTcGru>::kBRowsPiece);
+        ok = ok && encode_2d(fn, &p->b_hh[l], p->whh_p[l], 3 * H, H, TcCfg<kTcGru>::kBRowsPiece);
     }
     if (!ok) {
         *why = "cuTensorMapEncodeTiled failed";
@@ -479,6 +567,27 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
         tc_plan_destroy(p);
         return false;
     }
+    auto occupancy = [&](auto kern, int cluster, int smem_bytes) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned) (cluster * p->num_sms));
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = (size_t) smem_bytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned) cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = p->num_sms / cluster; }
+        return n;
+    };
+    p->max_clusters[kTcEnc] = occupancy(tc_masknet_kernel<kTcEnc>, TcCfg<kTcEnc>::kCluster, TcCfg<kTcEnc>::kSmemBytes);
+    p->max_clusters[kTcGru] = occupancy(tc_masknet_kernel<kTcGru>, TcCfg<kTcGru>::kCluster, TcCfg<kTcGru>::kSmemBytes);
+    p->max_clusters[kTcDec] = occupancy(tc_masknet_kernel<kTcDec>, TcCfg<kTcDec>::kCluster, TcCfg<kTcDec>::kSmemBytes);
+    const char *tr = getenv("KOALA_TC_TRACE");
+    if (tr && *tr == '1') {
+        if (cudaMalloc((void **) &p->trace, 1024 * sizeof(long long)) != cudaSuccess) p->trace = nullptr;
+        else cudaMemset(p->trace, 0, 1024 * sizeof(long long));
+    }
     *out = p;
     return true;
 }
@@ -488,32 +597,40 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
     const TcModel &m = p->m;
     const int nxt = cur ^ 1, H = m.H, mt = m.Bp / kTcPairM;
     const size_t LBH = (size_t) m.Bp * H;
-    const int max_pairs = p->num_sms / 2;
-    auto grid = [&](int tiles) { return 2 * (tiles < max_pairs ? tiles : max_pairs); };   // CTAs: one pair per tile slot
+    // persistent grid: one cluster per cluster-tile slot, capped by what the device can keep resident
+    auto grid = [&](int mode, int cluster, int ctiles) {
+        const int c = ctiles < p->max_clusters[mode] ? ctiles : p->max_clusters[mode];
+        return cluster * (c < 1 ? 1 : c);
+    };
     {
+        using C = TcCfg<kTcEnc>;
         TcArgs a{};
         a.num_m_tiles = mt; a.num_n_tiles = H / 256; a.kb_per_part = kBins / kTcBlockK; a.H = H;
         a.bias0 = m.enc_b; a.out_bf16 = m.e;
         if (prof) prof->begin(kKernEnc, st);
-        tc_masknet_kernel<kTcEnc><<<grid(mt * a.num_n_tiles), kTcThreads, TcCfg<kTcEnc>::kSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, a);
+        tc_masknet_kernel<kTcEnc><<<grid(kTcEnc, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, a);
         if (prof) prof->end(st);
     }
     for (int l = 0; l < m.L; l++) {
+        using C = TcCfg<kTcGru>;
         TcArgs a{};
         a.num_m_tiles = mt; a.num_n_tiles = H / kGruUnits; a.kb_per_part = H / kTcBlockK; a.H = H;
         a.bias0 = m.bih[l]; a.bias1 = m.bhh[l];
         a.h_prev = m.h[cur] + l * LBH; a.h_next = m.h[nxt] + l * LBH; a.out_bf16 = m.hb[nxt] + l * LBH;
+        a.trace = l == 0 ? p->trace : nullptr;
         const CUtensorMap &ax = l == 0 ? p->a_e : p->a_hb[nxt][l - 1];
         if (prof) prof->begin(kKernGru, st);
-        tc_masknet_kernel<kTcGru><<<grid(mt * a.num_n_tiles), kTcThreads, TcCfg<kTcGru>::kSmemBytes, st>>>(ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], a);
+        tc_masknet_kernel<kTcGru><<<grid(kTcGru, C::kCluster, (mt / C::kPM) * (a.num_n_tiles / C::kPN)), kTcThreads, C::kSmemBytes, st>>>(
+            ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], a);
         if (prof) prof->end(st);
     }
     {
+        using C = TcCfg<kTcDec>;
         TcArgs a{};
         a.num_m_tiles = mt; a.num_n_tiles = kBins / 256; a.kb_per_part = H / kTcBlockK; a.H = H;
         a.bias0 = m.dec_b; a.out_f32 = m.mask;
         if (prof) prof->begin(kKernDec, st);
-        tc_masknet_kernel<kTcDec><<<grid(mt * a.num_n_tiles), kTcThreads, TcCfg<kTcDec>::kSmemBytes, st>>>(p->a_hb[nxt][m.L - 1], p->a_hb[nxt][m.L - 1], p->b_dec, p->b_dec, a);
+        tc_masknet_kernel<kTcDec><<<grid(kTcDec, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_hb_dec[nxt], p->a_hb_dec[nxt], p->b_dec, p->b_dec, a);
         if (prof) prof->end(st);
     }
     return 2 + m.L;
