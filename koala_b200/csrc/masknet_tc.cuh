@@ -55,8 +55,12 @@ template <int MODE> struct TcCfg {
     static constexpr int kARowsPiece = kTcBlockM / kPN;                  // rows of A this CTA fetches (and multicasts)
     static constexpr int kBRowsPiece = kBRowsHalf / kPM;                 // rows of B this CTA fetches (and multicasts)
     static constexpr int kStageBytes = kTcABytes + kBRowsHalf * 128;     // 28 KB | 32 KB landing per CTA per stage
-    static constexpr int kStages = kGru ? 7 : 6;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kTcTailBytes;
+    static constexpr int kStages = 6;
+    // GRU only: the epilogue's h tile travels by TMA too (coalesced, off the LSU): fp32 h(t-1) lands in kEpiF32Bytes, is
+    // replaced in place by h(t), and the bf16 copy of h(t) is staged in kEpiBf16Bytes; both leave through TMA stores
+    static constexpr int kEpiF32Bytes = kGru ? kTcBlockM * kGruUnits * 4 : 0;     // 32 KB: two 128B-swizzled boxes of 32 floats
+    static constexpr int kEpiBf16Bytes = kGru ? kTcBlockM * kGruUnits * 2 : 0;    // 16 KB: one 128B-swizzled box of 64 bf16
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiF32Bytes + kEpiBf16Bytes + kTcTailBytes;
 };
 
 struct TcArgs {
@@ -70,6 +74,7 @@ struct TcArgs {
     __nv_bfloat16 *out_bf16;    // enc: e [Bp][H]; GRU: bf16 copy of h_next
     float *out_f32;             // dec: mask [Bp][256]
     long long *trace;           // optional clock64() timeline of CTAs 0 and 1 (KOALA_TC_TRACE=1), else nullptr
+    int debug_flags;            // timing experiments only (KOALA_TC_DEBUG): 1 = skip the epilogue's global loads / stores
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -119,6 +124,21 @@ __device__ __forceinline__ void tma_load_2d_pair_mc(const CUtensorMap *map, uint
         "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
+// CTA-local tile load (completion on a barrier of this CTA) and tile store (bulk async-group completion)
+__device__ __forceinline__ void tma_load_2d_local(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -193,7 +213,9 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float *f) {
 template <int MODE>
 __global__ void __cluster_dims__(TcCfg<MODE>::kCluster, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                  const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1, const TcArgs args) {
+                  const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
+                  const __grid_constant__ CUtensorMap map_hp, const __grid_constant__ CUtensorMap map_hn,
+                  const __grid_constant__ CUtensorMap map_hb, const TcArgs args) {
     using Cfg = TcCfg<MODE>;
     constexpr bool kGru = Cfg::kGru;
     constexpr int kStages = Cfg::kStages, kStageBytes = Cfg::kStageBytes, kBRowsHalf = Cfg::kBRowsHalf;
@@ -202,11 +224,15 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint8_t *s_hp = smem + kStages * kStageBytes;                 // GRU: fp32 h tile, boxes [128 rows][32 floats] x 2
+    uint8_t *s_hb = s_hp + Cfg::kEpiF32Bytes;                     // GRU: bf16 h(t) tile, box [128 rows][64 bf16]
+    uint8_t *tail = s_hb + Cfg::kEpiBf16Bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
     uint64_t *full_bar = bars, *empty_bar = bars + kStages;
     uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
-    float *s_bias = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256);   // [2 accumulator buffers][256]
+    uint64_t *hp_full = bars + 2 * kStages + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 5);
+    float *s_bias = reinterpret_cast<float *>(tail + 256);        // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();      // rank in the cluster = 2 * pair + position in pair
@@ -225,6 +251,9 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         if (kGru) {
             prefetch_tmap(&map_a1);
             prefetch_tmap(&map_b1);
+            prefetch_tmap(&map_hp);
+            prefetch_tmap(&map_hn);
+            prefetch_tmap(&map_hb);
         }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);     // leader's copy is the one in use: 1 arrive.expect_tx + 2 CTAs' TMA bytes
@@ -234,6 +263,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             mbar_init(&tmem_full[b], 1);    // one multicast tcgen05.commit
             mbar_init(&tmem_empty[b], 512); // leader's copy: 256 epilogue threads of each CTA
         }
+        mbar_init(hp_full, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * kTcAccCols);
@@ -347,27 +377,27 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         mbar_arrive_cluster(empty_leader[0]);
         mbar_arrive_cluster(empty_leader[1]);
 
+        // GRU: the h(t-1) tile of my first tile starts travelling now (one thread drives the epilogue's TMA traffic)
+        const int row_in_cta = quarter * 32 + lane;
+        if (kGru && te == 0 && cluster_id < num_tiles) {
+            const int m0 = (cluster_id / ctiles_n) * kPM + qm, n0 = (cluster_id % ctiles_n) * kPN + qn;
+            mbar_expect_tx(hp_full, Cfg::kEpiF32Bytes);
+            tma_load_2d_local(&map_hp, hp_full, s_hp, n0 * kGruUnits, m0 * kTcPairM + (int) rank * kTcBlockM);
+            tma_load_2d_local(&map_hp, hp_full, s_hp + Cfg::kEpiF32Bytes / 2, n0 * kGruUnits + 32, m0 * kTcPairM + (int) rank * kTcBlockM);
+        }
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             const int m = (tile / ctiles_n) * kPM + qm, n = (tile % ctiles_n) * kPN + qn;
             const int ab = it & 1, aphase = (it >> 1) & 1;
-            const size_t row = (size_t) m * kTcPairM + rank * kTcBlockM + quarter * 32 + lane;
+            const size_t row = (size_t) m * kTcPairM + rank * kTcBlockM + row_in_cta;
             float *sb = s_bias + ab * 256;
-            float hp[32];
             if (kGru) {
-                // biases of this tile -> smem ([n_x | r | z | n_h] x 64, same order as the TMEM columns), previous state
-                // of my 32 units -> registers; both are independent of the MMAs and fetched before the accumulator wait
+                // biases of this tile -> smem ([n_x | r | z | n_h] x 64, same order as the TMEM columns)
                 const int H = args.H, g = te >> 6, u = n * kGruUnits + (te & 63);
                 sb[te] = g == 0 ? __ldg(args.bias0 + 2 * H + u)
                        : g == 1 ? __ldg(args.bias0 + u) + __ldg(args.bias1 + u)
                        : g == 2 ? __ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u)
                                 : __ldg(args.bias1 + 2 * H + u);
-                const float4 *hp4 = reinterpret_cast<const float4 *>(args.h_prev + row * H + n * kGruUnits + half * 32);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 t = hp4[q];
-                    hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
-                }
             } else {
                 sb[te] = __ldg(args.bias0 + n * 256 + te);
             }
@@ -378,7 +408,12 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             if (te == 0) KTRACE(it * 48 + 5);
             const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (kGru) {
-                const int H = args.H;
+                mbar_wait(hp_full, it & 1);                      // h(t-1) tile has landed in s_hp
+                // 128B-swizzled tiles: 16-byte chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4); my 32 units are one
+                // fp32 box (8 chunks) and half of the bf16 box (chunks 4 * half .. 4 * half + 3)
+                uint8_t *hp_row = s_hp + half * (Cfg::kEpiF32Bytes / 2) + row_in_cta * 128;
+                uint8_t *hb_row = s_hb + row_in_cta * 128;
+                const int sw = row_in_cta & 7;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int cu = half * 32 + c * 16;           // first unit of this chunk inside the tile
@@ -387,6 +422,12 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                     tmem_ld16(t0 + 64 + cu, ar);
                     tmem_ld16(t0 + 128 + cu, az);
                     tmem_ld16(t0 + 192 + cu, anh);
+                    float hp[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 t = *reinterpret_cast<const float4 *>(hp_row + (((c * 4 + q) ^ sw) << 4));
+                        hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
+                    }
                     tmem_ld_wait();
                     tmem_zero16(t0 + 192 + cu);                  // n_h columns must be zero when the buffer is reused
 #pragma unroll
@@ -398,17 +439,40 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                         const float ip = __fdividef(1.0f, pr * pz);
                         const float rg = pz * ip, zg = pr * ip;
                         const float ng = tanh_f(anx[i] + sb[cu + i] + rg * (anh[i] + sb[192 + cu + i]));
-                        hn[i] = (1.0f - zg) * ng + zg * hp[c * 16 + i];
+                        hn[i] = (1.0f - zg) * ng + zg * hp[i];
                     }
-                    const size_t off = row * H + n * kGruUnits + cu;
-                    float4 *ho4 = reinterpret_cast<float4 *>(args.h_next + off);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) ho4[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
-                    uint4 *hb4 = reinterpret_cast<uint4 *>(args.out_bf16 + off);
-                    hb4[0] = pack_bf16x8(hn);
-                    hb4[1] = pack_bf16x8(hn + 8);
+                    for (int q = 0; q < 4; ++q)                  // h(t) replaces h(t-1) in place
+                        *reinterpret_cast<float4 *>(hp_row + (((c * 4 + q) ^ sw) << 4)) =
+                            make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+                    *reinterpret_cast<uint4 *>(hb_row + (((half * 4 + c * 2) ^ sw) << 4)) = pack_bf16x8(hn);
+                    *reinterpret_cast<uint4 *>(hb_row + (((half * 4 + c * 2 + 1) ^ sw) << 4)) = pack_bf16x8(hn + 8);
                 }
                 tmem_st_wait();
+                tc_fence_before();
+                if (te == 0) KTRACE(it * 48 + 6);
+                mbar_arrive_cluster(empty_leader[ab]);           // accumulator buffer back to the MMA issuer before the stores
+                fence_proxy_async();                             // my smem writes -> visible to the TMA engine
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (te == 0) {
+                    const int r0 = m * kTcPairM + (int) rank * kTcBlockM, u0 = n * kGruUnits;
+                    tma_store_2d(&map_hn, s_hp, u0, r0);
+                    tma_store_2d(&map_hn, s_hp + Cfg::kEpiF32Bytes / 2, u0 + 32, r0);
+                    tma_store_2d(&map_hb, s_hb, u0, r0);
+                    bulk_commit();
+                    const int next = tile + num_clusters;
+                    if (next < num_tiles) {                      // next tile's h(t-1) may overwrite s_hp once the stores have read it
+                        bulk_wait_read();
+                        const int m1 = (next / ctiles_n) * kPM + qm, n1 = (next % ctiles_n) * kPN + qn;
+                        mbar_expect_tx(hp_full, Cfg::kEpiF32Bytes);
+                        tma_load_2d_local(&map_hp, hp_full, s_hp, n1 * kGruUnits, m1 * kTcPairM + (int) rank * kTcBlockM);
+                        tma_load_2d_local(&map_hp, hp_full, s_hp + Cfg::kEpiF32Bytes / 2, n1 * kGruUnits + 32, m1 * kTcPairM + (int) rank * kTcBlockM);
+                    } else {
+                        bulk_wait_all();                         // smem must outlive the last stores
+                    }
+                    KTRACE(it * 48 + 7);
+                }
+                continue;
             } else {
                 const int N = args.num_n_tiles * 256;
 #pragma unroll 2
@@ -477,10 +541,13 @@ struct TcPlan {
     TcModel m;
     int num_sms = 0;
     long long *trace = nullptr;   // 2 x 512 clock64 slots, filled by the first GRU layer when KOALA_TC_TRACE=1
+    int debug_flags = 0;
     __nv_bfloat16 *wih_p[kMaxLayers] = {}, *whh_p[kMaxLayers] = {};
     CUtensorMap a_feat, a_hb_dec[2];                    // linear kernels: activation operands [Bp][K], box 64 x 128
     CUtensorMap a_e, a_hb[2][kMaxLayers];               // GRU kernel: box 64 x (128 / PN)
     CUtensorMap b_enc, b_dec, b_ih[kMaxLayers], b_hh[kMaxLayers];
+    CUtensorMap hf[2][kMaxLayers];                      // GRU epilogue: fp32 state [Bp][H], box 32 floats x 128 rows
+    CUtensorMap hb128[2][kMaxLayers];                   // GRU epilogue: bf16 state store, box 64 x 128
     int max_clusters[3] = {0, 0, 0};                    // co-resident clusters per kernel (cudaOccupancyMaxActiveClusters)
 };
 
@@ -488,12 +555,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool encode_2d(EncodeTiledFn fn, CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// [rows][cols] row-major matrix, box = 128 bytes x box_rows, 128B swizzle; bf16 (64 elements per box row) or fp32 (32)
+static bool encode_2d(EncodeTiledFn fn, CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      bool f32 = false) {
     const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * 2};
-    const cuuint32_t box[2] = {(cuuint32_t) kTcBlockK, box_rows};
+    const cuuint64_t strides[1] = {cols * (f32 ? 4 : 2)};
+    const cuuint32_t box[2] = {(cuuint32_t) (f32 ? 32 : kTcBlockK), box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    return fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -547,6 +616,10 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
         for (int l = 0; l < m.L; l++)
             ok = ok && encode_2d(fn, &p->a_hb[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, TcCfg<kTcGru>::kARowsPiece);
         ok = ok && encode_2d(fn, &p->a_hb_dec[par], m.hb[par] + (size_t) (m.L - 1) * Bp * H, Bp, H, kTcBlockM);
+        for (int l = 0; l < m.L; l++) {
+            ok = ok && encode_2d(fn, &p->hf[par][l], m.h[par] + (size_t) l * Bp * H, Bp, H, kTcBlockM, true);
+            ok = ok && encode_2d(fn, &p->hb128[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, kTcBlockM);
+        }
     }
     ok = ok && encode_2d(fn, &p->b_enc, m.enc_w, H, kBins, TcCfg<kTcEnc>::kBRowsHalf);
     ok = ok && encode_2d(fn, &p->b_dec, m.dec_w, kBins, H, TcCfg<kTcDec>::kBRowsHalf);
@@ -583,6 +656,8 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
     p->max_clusters[kTcEnc] = occupancy(tc_masknet_kernel<kTcEnc>, TcCfg<kTcEnc>::kCluster, TcCfg<kTcEnc>::kSmemBytes);
     p->max_clusters[kTcGru] = occupancy(tc_masknet_kernel<kTcGru>, TcCfg<kTcGru>::kCluster, TcCfg<kTcGru>::kSmemBytes);
     p->max_clusters[kTcDec] = occupancy(tc_masknet_kernel<kTcDec>, TcCfg<kTcDec>::kCluster, TcCfg<kTcDec>::kSmemBytes);
+    const char *dbg = getenv("KOALA_TC_DEBUG");
+    p->debug_flags = dbg ? atoi(dbg) : 0;
     const char *tr = getenv("KOALA_TC_TRACE");
     if (tr && *tr == '1') {
         if (cudaMalloc((void **) &p->trace, 1024 * sizeof(long long)) != cudaSuccess) p->trace = nullptr;
@@ -608,7 +683,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.num_m_tiles = mt; a.num_n_tiles = H / 256; a.kb_per_part = kBins / kTcBlockK; a.H = H;
         a.bias0 = m.enc_b; a.out_bf16 = m.e;
         if (prof) prof->begin(kKernEnc, st);
-        tc_masknet_kernel<kTcEnc><<<grid(kTcEnc, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, a);
+        tc_masknet_kernel<kTcEnc><<<grid(kTcEnc, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, p->a_feat, p->a_feat, p->a_feat, a);
         if (prof) prof->end(st);
     }
     for (int l = 0; l < m.L; l++) {
@@ -618,10 +693,11 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.bias0 = m.bih[l]; a.bias1 = m.bhh[l];
         a.h_prev = m.h[cur] + l * LBH; a.h_next = m.h[nxt] + l * LBH; a.out_bf16 = m.hb[nxt] + l * LBH;
         a.trace = l == 0 ? p->trace : nullptr;
+        a.debug_flags = p->debug_flags;
         const CUtensorMap &ax = l == 0 ? p->a_e : p->a_hb[nxt][l - 1];
         if (prof) prof->begin(kKernGru, st);
         tc_masknet_kernel<kTcGru><<<grid(kTcGru, C::kCluster, (mt / C::kPM) * (a.num_n_tiles / C::kPN)), kTcThreads, C::kSmemBytes, st>>>(
-            ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], a);
+            ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], p->hf[cur][l], p->hf[nxt][l], p->hb128[nxt][l], a);
         if (prof) prof->end(st);
     }
     {
@@ -630,7 +706,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.num_m_tiles = mt; a.num_n_tiles = kBins / 256; a.kb_per_part = H / kTcBlockK; a.H = H;
         a.bias0 = m.dec_b; a.out_f32 = m.mask;
         if (prof) prof->begin(kKernDec, st);
-        tc_masknet_kernel<kTcDec><<<grid(kTcDec, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_hb_dec[nxt], p->a_hb_dec[nxt], p->b_dec, p->b_dec, a);
+        tc_masknet_kernel<kTcDec><<<grid(kTcDec, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_hb_dec[nxt], p->a_hb_dec[nxt], p->b_dec, p->b_dec, p->a_feat, p->a_feat, p->a_feat, a);
         if (prof) prof->end(st);
     }
     return 2 + m.L;
