@@ -19,7 +19,7 @@
 //   h-part (K = H): one N=192 MMA per k-step, packed W_hh rows ordered r|z|n, D column base  64 -> r, z (accumulated), n_h
 //   n_h has no zero-initialising MMA of its own (the accumulate flag is per instruction), so the epilogue clears those
 //   64 columns with tcgen05.st before it hands the buffer back.
-// Linear tile = 256 streams x 256 outputs, one N=256 MMA per k-step.
+// Linear tile = 256 streams x 128 outputs, one N=128 MMA per k-step; the output tile is staged in smem and TMA-stored.
 #pragma once
 
 #include <cuda.h>
@@ -51,15 +51,17 @@ template <int MODE> struct TcCfg {
     static constexpr bool kGru = MODE == kTcGru;
     static constexpr int kPM = 1, kPN = kGru ? 2 : 1;   // GRU: 4-CTA clusters, activations multicast across 2 unit tiles
     static constexpr int kPairs = kPM * kPN, kCluster = 2 * kPairs;
-    static constexpr int kBRowsHalf = kGru ? kGruRows / 2 : 128;        // weight rows each CTA of a pair holds
+    static constexpr int kLinN = 128;                                   // outputs per linear pair-tile (one N=128 MMA per k-step)
+    static constexpr int kBRowsHalf = kGru ? kGruRows / 2 : kLinN / 2;  // weight rows each CTA of a pair holds
     static constexpr int kARowsPiece = kTcBlockM / kPN;                  // rows of A this CTA fetches (and multicasts)
     static constexpr int kBRowsPiece = kBRowsHalf / kPM;                 // rows of B this CTA fetches (and multicasts)
-    static constexpr int kStageBytes = kTcABytes + kBRowsHalf * 128;     // 28 KB | 32 KB landing per CTA per stage
-    static constexpr int kStages = 6;
+    static constexpr int kStageBytes = kTcABytes + kBRowsHalf * 128;     // 28 KB | 24 KB landing per CTA per stage
+    static constexpr int kStages = kGru ? 6 : 4;
     // GRU only: the epilogue's h tile travels by TMA too (coalesced, off the LSU): fp32 h(t-1) lands in kEpiF32Bytes, is
     // replaced in place by h(t), and the bf16 copy of h(t) is staged in kEpiBf16Bytes; both leave through TMA stores
-    static constexpr int kEpiF32Bytes = kGru ? kTcBlockM * kGruUnits * 4 : 0;     // 32 KB: two 128B-swizzled boxes of 32 floats
-    static constexpr int kEpiBf16Bytes = kGru ? kTcBlockM * kGruUnits * 2 : 0;    // 16 KB: one 128B-swizzled box of 64 bf16
+    // Linear kernels stage their [128 x 128] output tile the same way (encoder: bf16, decoder: fp32) and TMA-store it.
+    static constexpr int kEpiF32Bytes = kGru ? kTcBlockM * kGruUnits * 4 : (MODE == kTcDec ? kTcBlockM * kLinN * 4 : 0);    // 128B-swizzled boxes of 32 floats
+    static constexpr int kEpiBf16Bytes = kGru ? kTcBlockM * kGruUnits * 2 : (MODE == kTcEnc ? kTcBlockM * kLinN * 2 : 0);  // 128B-swizzled boxes of 64 bf16
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiF32Bytes + kEpiBf16Bytes + kTcTailBytes;
 };
 
@@ -254,6 +256,8 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             prefetch_tmap(&map_hp);
             prefetch_tmap(&map_hn);
             prefetch_tmap(&map_hb);
+        } else {
+            prefetch_tmap(&map_hn);    // linear kernels: the output tile's store map
         }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);     // leader's copy is the one in use: 1 arrive.expect_tx + 2 CTAs' TMA bytes
@@ -343,7 +347,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
                     for (int k = 0; k < kTcBlockK / 16; ++k) {
                         const uint64_t ad = adesc + 2 * k, bd = bdesc + 2 * k;   // +32 B per 16-element k-step
-                        if (!kGru) umma_bf16_pair(d, ad, bd, make_idesc(256, 256), (kb | k) != 0);
+                        if (!kGru) umma_bf16_pair(d, ad, bd, make_idesc(256, Cfg::kLinN), (kb | k) != 0);
                         else if (kb < args.kb_per_part) umma_bf16_pair(d, ad, bd, make_idesc(256, kGruRows), (kb | k) != 0);
                         else umma_bf16_pair(d + kGruUnits, ad, bd, make_idesc(256, kGruRows), 1u);
                     }
@@ -399,7 +403,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                        : g == 2 ? __ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u)
                                 : __ldg(args.bias1 + 2 * H + u);
             } else {
-                sb[te] = __ldg(args.bias0 + n * 256 + te);
+                if (te < Cfg::kLinN) sb[te] = __ldg(args.bias0 + n * Cfg::kLinN + te);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");   // the 256 epilogue threads only
             if (te == 0) KTRACE(it * 48 + 4);
@@ -474,10 +478,11 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 }
                 continue;
             } else {
-                const int N = args.num_n_tiles * 256;
-#pragma unroll 2
-                for (int c = 0; c < 8; ++c) {
-                    const int cc = half * 128 + c * 16;
+                // my 64 of the tile's 128 outputs: bias + activation, staged in 128B-swizzled smem boxes, stored by TMA
+                const int sw = row_in_cta & 7;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int cc = half * 64 + c * 16;
                     float acc[16];
                     tmem_ld16(t0 + cc, acc);
                     tmem_ld_wait();
@@ -486,22 +491,38 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                         const float v = acc[i] + sb[cc + i];
                         acc[i] = MODE == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
                     }
-                    const size_t off = row * N + n * 256 + cc;
-                    if (MODE == kTcEnc) {
-                        uint4 *o = reinterpret_cast<uint4 *>(args.out_bf16 + off);
-                        o[0] = pack_bf16x8(acc);
-                        o[1] = pack_bf16x8(acc + 8);
-                    } else {
-                        float4 *o = reinterpret_cast<float4 *>(args.out_f32 + off);
+                    if (MODE == kTcEnc) {        // bf16: box `half` = [128 rows][64 bf16], my chunk pair 2c, 2c+1
+                        uint8_t *rowp = s_hb + half * (kTcBlockM * 128) + row_in_cta * 128;
+                        *reinterpret_cast<uint4 *>(rowp + (((2 * c) ^ sw) << 4)) = pack_bf16x8(acc);
+                        *reinterpret_cast<uint4 *>(rowp + (((2 * c + 1) ^ sw) << 4)) = pack_bf16x8(acc + 8);
+                    } else {                     // fp32: box 2 * half + c / 2 = [128 rows][32 floats], my chunks 4 (c & 1) + q
+                        uint8_t *rowp = s_hp + (2 * half + (c >> 1)) * (kTcBlockM * 128) + row_in_cta * 128;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4 *>(rowp + (((4 * (c & 1) + q) ^ sw) << 4)) =
+                                make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
                     }
                 }
+                tc_fence_before();
+                if (te == 0) KTRACE(it * 48 + 6);
+                mbar_arrive_cluster(empty_leader[ab]);
+                fence_proxy_async();
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (te == 0) {
+                    const int r0 = m * kTcPairM + (int) rank * kTcBlockM, c0 = n * Cfg::kLinN;
+                    if (MODE == kTcEnc) {
+                        tma_store_2d(&map_hn, s_hb, c0, r0);
+                        tma_store_2d(&map_hn, s_hb + kTcBlockM * 128, c0 + 64, r0);
+                    } else {
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; ++b4) tma_store_2d(&map_hn, s_hp + b4 * (kTcBlockM * 128), c0 + 32 * b4, r0);
+                    }
+                    bulk_commit();
+                    if (tile + num_clusters < num_tiles) bulk_wait_read();   // staging is rewritten by my next tile
+                    else bulk_wait_all();
+                    KTRACE(it * 48 + 7);
+                }
             }
-            tc_fence_before();
-            if (te == 0) KTRACE(it * 48 + 6);
-            mbar_arrive_cluster(empty_leader[ab]);
-            if (te == 0) KTRACE(it * 48 + 7);
         }
     }
     if (threadIdx.x == 0) KTRACE(502);
@@ -540,12 +561,14 @@ struct TcModel {
 struct TcPlan {
     TcModel m;
     int num_sms = 0;
-    long long *trace = nullptr;   // 2 x 512 clock64 slots, filled by the first GRU layer when KOALA_TC_TRACE=1
+    long long *trace = nullptr;   // 2 x 512 clock64 slots, filled by one kernel: KOALA_TC_TRACE=1 GRU layer 0, 2 decoder, 3 encoder
+    int trace_kernel = 0;
     int debug_flags = 0;
     __nv_bfloat16 *wih_p[kMaxLayers] = {}, *whh_p[kMaxLayers] = {};
     CUtensorMap a_feat, a_hb_dec[2];                    // linear kernels: activation operands [Bp][K], box 64 x 128
     CUtensorMap a_e, a_hb[2][kMaxLayers];               // GRU kernel: box 64 x (128 / PN)
     CUtensorMap b_enc, b_dec, b_ih[kMaxLayers], b_hh[kMaxLayers];
+    CUtensorMap e128, mask_f32;                         // linear epilogues: encoder output bf16 box 64 x 128, mask fp32 box 32 x 128
     CUtensorMap hf[2][kMaxLayers];                      // GRU epilogue: fp32 state [Bp][H], box 32 floats x 128 rows
     CUtensorMap hb128[2][kMaxLayers];                   // GRU epilogue: bf16 state store, box 64 x 128
     int max_clusters[3] = {0, 0, 0};                    // co-resident clusters per kernel (cudaOccupancyMaxActiveClusters)
@@ -612,6 +635,8 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
     }
     ok = ok && encode_2d(fn, &p->a_feat, m.feat, Bp, kBins, kTcBlockM);
     ok = ok && encode_2d(fn, &p->a_e, m.e, Bp, H, TcCfg<kTcGru>::kARowsPiece);
+    ok = ok && encode_2d(fn, &p->e128, m.e, Bp, H, kTcBlockM);
+    ok = ok && encode_2d(fn, &p->mask_f32, m.mask, Bp, kBins, kTcBlockM, true);
     for (int par = 0; par < 2; par++) {
         for (int l = 0; l < m.L; l++)
             ok = ok && encode_2d(fn, &p->a_hb[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, TcCfg<kTcGru>::kARowsPiece);
@@ -659,7 +684,8 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
     const char *dbg = getenv("KOALA_TC_DEBUG");
     p->debug_flags = dbg ? atoi(dbg) : 0;
     const char *tr = getenv("KOALA_TC_TRACE");
-    if (tr && *tr == '1') {
+    if (tr && *tr >= '1' && *tr <= '3') {
+        p->trace_kernel = *tr - '0';
         if (cudaMalloc((void **) &p->trace, 1024 * sizeof(long long)) != cudaSuccess) p->trace = nullptr;
         else cudaMemset(p->trace, 0, 1024 * sizeof(long long));
     }
@@ -680,10 +706,11 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
     {
         using C = TcCfg<kTcEnc>;
         TcArgs a{};
-        a.num_m_tiles = mt; a.num_n_tiles = H / 256; a.kb_per_part = kBins / kTcBlockK; a.H = H;
+        a.num_m_tiles = mt; a.num_n_tiles = H / C::kLinN; a.kb_per_part = kBins / kTcBlockK; a.H = H;
         a.bias0 = m.enc_b; a.out_bf16 = m.e;
+        a.trace = p->trace_kernel == 3 ? p->trace : nullptr;
         if (prof) prof->begin(kKernEnc, st);
-        tc_masknet_kernel<kTcEnc><<<grid(kTcEnc, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, p->a_feat, p->a_feat, p->a_feat, a);
+        tc_masknet_kernel<kTcEnc><<<grid(kTcEnc, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, p->a_feat, p->e128, p->a_feat, a);
         if (prof) prof->end(st);
     }
     for (int l = 0; l < m.L; l++) {
@@ -692,7 +719,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.num_m_tiles = mt; a.num_n_tiles = H / kGruUnits; a.kb_per_part = H / kTcBlockK; a.H = H;
         a.bias0 = m.bih[l]; a.bias1 = m.bhh[l];
         a.h_prev = m.h[cur] + l * LBH; a.h_next = m.h[nxt] + l * LBH; a.out_bf16 = m.hb[nxt] + l * LBH;
-        a.trace = l == 0 ? p->trace : nullptr;
+        a.trace = (l == 0 && p->trace_kernel == 1) ? p->trace : nullptr;
         a.debug_flags = p->debug_flags;
         const CUtensorMap &ax = l == 0 ? p->a_e : p->a_hb[nxt][l - 1];
         if (prof) prof->begin(kKernGru, st);
@@ -703,10 +730,11 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
     {
         using C = TcCfg<kTcDec>;
         TcArgs a{};
-        a.num_m_tiles = mt; a.num_n_tiles = kBins / 256; a.kb_per_part = H / kTcBlockK; a.H = H;
+        a.num_m_tiles = mt; a.num_n_tiles = kBins / C::kLinN; a.kb_per_part = H / kTcBlockK; a.H = H;
         a.bias0 = m.dec_b; a.out_f32 = m.mask;
+        a.trace = p->trace_kernel == 2 ? p->trace : nullptr;
         if (prof) prof->begin(kKernDec, st);
-        tc_masknet_kernel<kTcDec><<<grid(kTcDec, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_hb_dec[nxt], p->a_hb_dec[nxt], p->b_dec, p->b_dec, p->a_feat, p->a_feat, p->a_feat, a);
+        tc_masknet_kernel<kTcDec><<<grid(kTcDec, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_hb_dec[nxt], p->a_hb_dec[nxt], p->b_dec, p->b_dec, p->a_feat, p->mask_f32, p->a_feat, a);
         if (prof) prof->end(st);
     }
     return 2 + m.L;

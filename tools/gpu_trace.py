@@ -1,7 +1,7 @@
 """Dump the clock64() timeline of one GRU launch (KOALA_TC_TRACE=1) -- development aid for the tcgen05 pipeline."""
 import os, sys
 import numpy as np
-os.environ["KOALA_TC_TRACE"] = "1"
+os.environ["KOALA_TC_TRACE"] = sys.argv[2] if len(sys.argv) > 2 else "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import koala_b200 as kb
 from koala_b200 import spec
