@@ -10,8 +10,8 @@
 // 64-wide k-block against ~400 cycles of MMA (profiles/r01_step_summary.md).  Sharing the weight tile between the two
 // SMs of a pair cuts that to 28 KB.
 //
-// One persistent CTA pair per 2 SMs, 10 warps per CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + (leader CTA only)
-// MMA issuer, warps 2-9 = epilogue (two warps per TMEM lane quarter, splitting the columns).  Two accumulator buffers of
+// One persistent CTA pair per 2 SMs, 21 warps per CTA: warps 0,1 / 3,4 = TMA producers (activations / weights, even / odd
+// k-blocks), warp 2 = TMEM allocator + (leader CTA only) MMA issuer, warps 5-20 = epilogue (four warps per TMEM lane quarter).  Two accumulator buffers of
 // 256 TMEM columns let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // GRU tile = 256 streams x 64 hidden units.  TMEM columns per buffer: [n_x 0..63 | r 64..127 | z 128..191 | n_h 192..255].
@@ -35,7 +35,9 @@ constexpr int kTcBlockM = 128;                // rows per CTA; a pair covers 256
 constexpr int kTcPairM = 256;
 constexpr int kTcBlockK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kTcABytes = kTcBlockM * 128;    // 16 KB
-constexpr int kTcThreads = 352;               // TMA warp (A) + MMA warp + 8 epilogue warps + TMA warp (B)
+constexpr int kTcEpiWarps = 16;               // 4 warps per TMEM lane quarter, each owning a quarter of the tile's columns
+constexpr int kTcEpiThreads = kTcEpiWarps * 32;
+constexpr int kTcThreads = 160 + kTcEpiThreads; // 2 TMA warps (A) + MMA warp + 2 TMA warps (B) + 16 epilogue warps
 constexpr int kTcAccCols = 256;
 constexpr int kGruUnits = 64;                 // hidden units per GRU tile
 constexpr int kGruRows = 3 * kGruUnits;       // packed weight rows per tile (both CTAs together)
@@ -56,13 +58,14 @@ template <int MODE> struct TcCfg {
     static constexpr int kARowsPiece = kTcBlockM / kPN;                  // rows of A this CTA fetches (and multicasts)
     static constexpr int kBRowsPiece = kBRowsHalf / kPM;                 // rows of B this CTA fetches (and multicasts)
     static constexpr int kStageBytes = kTcABytes + kBRowsHalf * 128;     // 28 KB | 24 KB landing per CTA per stage
-    static constexpr int kStages = kGru ? 6 : 4;
+    static constexpr int kStages = kGru ? 5 : 4;
     // GRU only: the epilogue's h tile travels by TMA too (coalesced, off the LSU): fp32 h(t-1) lands in kEpiF32Bytes, is
     // replaced in place by h(t), and the bf16 copy of h(t) is staged in kEpiBf16Bytes; both leave through TMA stores
     // Linear kernels stage their [128 x 128] output tile the same way (encoder: bf16, decoder: fp32) and TMA-store it.
     static constexpr int kEpiF32Bytes = kGru ? kTcBlockM * kGruUnits * 4 : (MODE == kTcDec ? kTcBlockM * kLinN * 4 : 0);    // 128B-swizzled boxes of 32 floats
     static constexpr int kEpiBf16Bytes = kGru ? kTcBlockM * kGruUnits * 2 : (MODE == kTcEnc ? kTcBlockM * kLinN * 2 : 0);  // 128B-swizzled boxes of 64 bf16
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiF32Bytes + kEpiBf16Bytes + kTcTailBytes;
+    static constexpr int kEpiF32Bufs = kGru ? 2 : 1;   // GRU: h(t-1) of the next tile lands while this tile's h(t) is being stored
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiF32Bufs * kEpiF32Bytes + kEpiBf16Bytes + kTcTailBytes;
 };
 
 struct TcArgs {
@@ -180,6 +183,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // clears 16 consecutive TMEM columns of this thread's lane
 __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
@@ -227,13 +252,13 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
     uint8_t *s_hp = smem + kStages * kStageBytes;                 // GRU: fp32 h tile, boxes [128 rows][32 floats] x 2
-    uint8_t *s_hb = s_hp + Cfg::kEpiF32Bytes;                     // GRU: bf16 h(t) tile, box [128 rows][64 bf16]
+    uint8_t *s_hb = s_hp + Cfg::kEpiF32Bufs * Cfg::kEpiF32Bytes;  // GRU: bf16 h(t) tile, box [128 rows][64 bf16]
     uint8_t *tail = s_hb + Cfg::kEpiBf16Bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
     uint64_t *full_bar = bars, *empty_bar = bars + kStages;
     uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
-    uint64_t *hp_full = bars + 2 * kStages + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 5);
+    uint64_t *hp_full = bars + 2 * kStages + 4;                   // [2]: one per fp32 tile buffer
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 6);
     float *s_bias = reinterpret_cast<float *>(tail + 256);        // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -265,12 +290,13 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);    // one multicast tcgen05.commit
-            mbar_init(&tmem_empty[b], 512); // leader's copy: 256 epilogue threads of each CTA
+            mbar_init(&tmem_empty[b], 2 * kTcEpiThreads); // leader's copy: the epilogue threads of both CTAs
         }
-        mbar_init(hp_full, 1);
+        mbar_init(&hp_full[0], 1);
+        mbar_init(&hp_full[1], 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * kTcAccCols);
+    if (warp == 2) tmem_alloc_pair(tmem_slot, 2 * kTcAccCols);
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -282,13 +308,16 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const int num_tiles = (args.num_m_tiles / kPM) * ctiles_n;
     const int num_kb = (kGru ? 2 : 1) * args.kb_per_part;
 
-    if (warp == 0 || warp == 10) {
-        // ===================================================== TMA producers (both CTAs of every pair).  One thread can
-        // issue a tensor load only every ~210 cycles whatever its size (tools/micro/tma_rate.cu), so the activation (A)
-        // and weight (B) tiles of a k-block are issued by two different warps: warp 0 loads A, warp 10 loads B.
+    if (warp == 0 || warp == 1 || warp == 3 || warp == 4) {
+        // ===================================================== TMA producers (both CTAs of every pair).  One warp can issue a
+        // tensor load only every ~210-380 cycles whatever its size (tools/micro/tma_rate.cu), about one MMA k-block, so
+        // the loads are spread over four warps: warps 0/1 fetch the activation (A) tiles of the even/odd k-blocks, warps
+        // 3/4 the weight (B) tiles.  Everything stays warp-uniform (elect_one) so descriptors live in uniform registers.
         {
-            const bool is_a = warp == 0;
-            int stage = 0, phase = 0, pit = 0;
+            const bool is_a = warp < 2;
+            const int par = is_a ? warp : warp - 3;             // my k-block parity
+            int pit = 0;
+            long long g = par;                                  // running k-block index across tiles -> stage / phase
             // multicast destinations: A goes to the CTAs with my (qm, position), B to those with my (qn, position)
             uint16_t mask_a = 0, mask_b = 0;
 #pragma unroll
@@ -297,8 +326,9 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             for (int j = 0; j < kPM; ++j) mask_b |= (uint16_t) (1u << (2 * (j + kPM * qn) + rank));
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++pit) {
                 const int m = (tile / ctiles_n) * kPM + qm, n = (tile % ctiles_n) * kPN + qn;
-                if (is_a && lane == 0) KTRACE(pit * 48 + 0);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                if (warp == 0 && lane == 0) KTRACE(pit * 48 + 0);
+                for (int kb = par; kb < num_kb; kb += 2, g += 2) {
+                    const int stage = (int) (g % kStages), phase = (int) ((g / kStages) & 1);
                     mbar_wait(&empty_bar[stage], phase ^ 1);     // slot free in every CTA of the cluster
                     if (is_a && lane == 0) KTRACE(pit * 48 + 16 + kb);
                     const bool elected = elect_one();
@@ -320,12 +350,11 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                         else tma_load_2d_pair(mb, full_leader, sb, kc, brow);
                     }
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                if (is_a && lane == 0) KTRACE(pit * 48 + 1);
+                if (warp == 0 && lane == 0) KTRACE(pit * 48 + 1);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 2) {
         // ===================================================== MMA issuer (one thread of the leader CTA drives both SMs)
         if (rank == 0) {
             int stage = 0, phase = 0, it = 0;
@@ -362,18 +391,20 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 if (lane == 0) KTRACE(it * 48 + 3);
             }
         }
-    } else if (warp < 10) {
-        // ===================================================== epilogue: warps 2..9; TMEM lane quarter = warp % 4, the two
-        // warps of a quarter split the columns (GRU: 32 of the 64 units each; linear: 128 of the 256 outputs each)
-        const int quarter = warp & 3, half = (warp - 2) >> 2, te = threadIdx.x - 64;   // warps 2..9 only
+    } else if (warp >= 5) {
+        // ===================================================== epilogue: warps 5..20.  TMEM lane quarter = warp % 4 (a warp can
+        // only touch its own 32 lanes); the 4 warps of a quarter split the tile's columns (GRU: 16 of the 64 units each,
+        // linear: 32 of the 128 outputs each) and work through them 8 at a time.  16 warps, not 8: the gate math is a long
+        // dependent chain (5 MUFU ops per unit) and needs the extra warps per scheduler to hide its latency.
+        const int quarter = warp & 3, part = (warp - 5) >> 2, te = threadIdx.x - 160;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
         uint32_t empty_leader[2] = {map_to_cta(&tmem_empty[0], leader), map_to_cta(&tmem_empty[1], leader)};
         // hand both buffers to the MMA issuer for the first time (GRU: with the n_h columns cleared)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             if (kGru) {
-                tmem_zero16(lane_base + b * kTcAccCols + 192 + half * 32);
-                tmem_zero16(lane_base + b * kTcAccCols + 192 + half * 32 + 16);
+                tmem_zero8(lane_base + b * kTcAccCols + 192 + part * 16);
+                tmem_zero8(lane_base + b * kTcAccCols + 192 + part * 16 + 8);
             }
         }
         if (kGru) tmem_st_wait();
@@ -383,131 +414,142 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
         // GRU: the h(t-1) tile of my first tile starts travelling now (one thread drives the epilogue's TMA traffic)
         const int row_in_cta = quarter * 32 + lane;
+        const int sw = row_in_cta & 7;
         if (kGru && te == 0 && cluster_id < num_tiles) {
             const int m0 = (cluster_id / ctiles_n) * kPM + qm, n0 = (cluster_id % ctiles_n) * kPN + qn;
-            mbar_expect_tx(hp_full, Cfg::kEpiF32Bytes);
-            tma_load_2d_local(&map_hp, hp_full, s_hp, n0 * kGruUnits, m0 * kTcPairM + (int) rank * kTcBlockM);
-            tma_load_2d_local(&map_hp, hp_full, s_hp + Cfg::kEpiF32Bytes / 2, n0 * kGruUnits + 32, m0 * kTcPairM + (int) rank * kTcBlockM);
+            mbar_expect_tx(&hp_full[0], Cfg::kEpiF32Bytes);
+            tma_load_2d_local(&map_hp, &hp_full[0], s_hp, n0 * kGruUnits, m0 * kTcPairM + (int) rank * kTcBlockM);
+            tma_load_2d_local(&map_hp, &hp_full[0], s_hp + Cfg::kEpiF32Bytes / 2, n0 * kGruUnits + 32, m0 * kTcPairM + (int) rank * kTcBlockM);
         }
+        constexpr float kL2e = 1.4426950408889634f;
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             const int m = (tile / ctiles_n) * kPM + qm, n = (tile % ctiles_n) * kPN + qn;
             const int ab = it & 1, aphase = (it >> 1) & 1;
-            const size_t row = (size_t) m * kTcPairM + rank * kTcBlockM + row_in_cta;
             float *sb = s_bias + ab * 256;
             if (kGru) {
-                // biases of this tile -> smem ([n_x | r | z | n_h] x 64, same order as the TMEM columns)
-                const int H = args.H, g = te >> 6, u = n * kGruUnits + (te & 63);
-                sb[te] = g == 0 ? __ldg(args.bias0 + 2 * H + u)
-                       : g == 1 ? __ldg(args.bias0 + u) + __ldg(args.bias1 + u)
-                       : g == 2 ? __ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u)
-                                : __ldg(args.bias1 + 2 * H + u);
+                // biases of this tile -> smem, ordered like the TMEM columns [n_x | r | z | n_h] x 64; the r and z biases are
+                // pre-multiplied by -log2(e) so that the sigmoid argument is one FFMA away from ex2
+                if (te < 256) {
+                    const int H = args.H, g = te >> 6, u = n * kGruUnits + (te & 63);
+                    sb[te] = g == 0 ? __ldg(args.bias0 + 2 * H + u)
+                           : g == 1 ? -kL2e * (__ldg(args.bias0 + u) + __ldg(args.bias1 + u))
+                           : g == 2 ? -kL2e * (__ldg(args.bias0 + H + u) + __ldg(args.bias1 + H + u))
+                                    : __ldg(args.bias1 + 2 * H + u);
+                }
             } else {
                 if (te < Cfg::kLinN) sb[te] = __ldg(args.bias0 + n * Cfg::kLinN + te);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // the 256 epilogue threads only
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");   // the epilogue threads only
             if (te == 0) KTRACE(it * 48 + 4);
             mbar_wait(&tmem_full[ab], aphase);
             tc_fence_after();
             if (te == 0) KTRACE(it * 48 + 5);
             const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (kGru) {
-                mbar_wait(hp_full, it & 1);                      // h(t-1) tile has landed in s_hp
-                // 128B-swizzled tiles: 16-byte chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4); my 32 units are one
-                // fp32 box (8 chunks) and half of the bf16 box (chunks 4 * half .. 4 * half + 3)
-                uint8_t *hp_row = s_hp + half * (Cfg::kEpiF32Bytes / 2) + row_in_cta * 128;
+                // fp32 tile buffers alternate per tile.  Before anything is written to shared memory again, the stores of the
+                // previous tile must have finished READING it (they were issued ~a whole mainloop ago); then the next tile's
+                // h(t-1) is requested into the other buffer so it is there when that tile's accumulator is.
+                uint8_t *hp_buf = s_hp + (it & 1) * Cfg::kEpiF32Bytes;
+                if (te == 0) {
+                    bulk_wait_read();
+                    const int next = tile + num_clusters;
+                    if (next < num_tiles) {
+                        uint8_t *nb = s_hp + ((it + 1) & 1) * Cfg::kEpiF32Bytes;
+                        uint64_t *nbar = &hp_full[(it + 1) & 1];
+                        const int m1 = (next / ctiles_n) * kPM + qm, n1 = (next % ctiles_n) * kPN + qn;
+                        mbar_expect_tx(nbar, Cfg::kEpiF32Bytes);
+                        tma_load_2d_local(&map_hp, nbar, nb, n1 * kGruUnits, m1 * kTcPairM + (int) rank * kTcBlockM);
+                        tma_load_2d_local(&map_hp, nbar, nb + Cfg::kEpiF32Bytes / 2, n1 * kGruUnits + 32, m1 * kTcPairM + (int) rank * kTcBlockM);
+                    }
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(kTcEpiThreads) : "memory");
+                mbar_wait(&hp_full[it & 1], (it >> 1) & 1);      // h(t-1) tile has landed
+                // 128B-swizzled tiles: 16-byte chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4).  My 16 units are half of
+                // an fp32 box row (4 chunks of 4 floats) and a quarter of the bf16 box row (2 chunks of 8)
+                uint8_t *hp_row = hp_buf + (part >> 1) * (Cfg::kEpiF32Bytes / 2) + row_in_cta * 128;
                 uint8_t *hb_row = s_hb + row_in_cta * 128;
-                const int sw = row_in_cta & 7;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const int cu = half * 32 + c * 16;           // first unit of this chunk inside the tile
-                    float anx[16], ar[16], az[16], anh[16], hn[16];
-                    tmem_ld16(t0 + 0 + cu, anx);
-                    tmem_ld16(t0 + 64 + cu, ar);
-                    tmem_ld16(t0 + 128 + cu, az);
-                    tmem_ld16(t0 + 192 + cu, anh);
-                    float hp[16];
+                    const int cu = part * 16 + c * 8;            // first of my 8 units inside the tile
+                    float anx[8], ar[8], az[8], anh[8], hp[8], hn[8];
+                    tmem_ld8(t0 + 0 + cu, anx);
+                    tmem_ld8(t0 + 64 + cu, ar);
+                    tmem_ld8(t0 + 128 + cu, az);
+                    tmem_ld8(t0 + 192 + cu, anh);
+                    const int ch = (part & 1) * 4 + c * 2;       // first of my 2 fp32 chunks in the box row
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 t = *reinterpret_cast<const float4 *>(hp_row + (((c * 4 + q) ^ sw) << 4));
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 t = *reinterpret_cast<const float4 *>(hp_row + (((ch + q) ^ sw) << 4));
                         hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
                     }
                     tmem_ld_wait();
-                    tmem_zero16(t0 + 192 + cu);                  // n_h columns must be zero when the buffer is reused
+                    if (te == 0) KTRACE(it * 48 + 8 + c * 2);
+                    tmem_zero8(t0 + 192 + cu);                   // n_h columns must be zero when the buffer is reused
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        // r = 1/(1+er), z = 1/(1+ez) with one shared reciprocal: 5 MUFU ops per unit instead of 6
-                        const float er = __expf(fminf(-(ar[i] + sb[64 + cu + i]), 30.0f));
-                        const float ez = __expf(fminf(-(az[i] + sb[128 + cu + i]), 30.0f));
+                    for (int i = 0; i < 8; ++i) {
+                        // r = 1/(1+er), z = 1/(1+ez) share one reciprocal: 5 MUFU ops per unit.  Arguments are clamped so that
+                        // (1+er)(1+ez) cannot overflow: sigmoid(-30) is already 9e-14.
+                        const float er = ex2_approx(fminf(fmaf(ar[i], -kL2e, sb[64 + cu + i]), 43.0f));
+                        const float ez = ex2_approx(fminf(fmaf(az[i], -kL2e, sb[128 + cu + i]), 43.0f));
                         const float pr = 1.0f + er, pz = 1.0f + ez;
-                        const float ip = __fdividef(1.0f, pr * pz);
+                        const float ip = rcp_approx(pr * pz);
                         const float rg = pz * ip, zg = pr * ip;
-                        const float ng = tanh_f(anx[i] + sb[cu + i] + rg * (anh[i] + sb[192 + cu + i]));
-                        hn[i] = (1.0f - zg) * ng + zg * hp[i];
+                        const float t = fmaf(rg, anh[i] + sb[192 + cu + i], anx[i] + sb[cu + i]);
+                        const float ng = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(t * (2.0f * kL2e))), 1.0f);   // tanh(t)
+                        hn[i] = fmaf(zg, hp[i] - ng, ng);        // (1 - z) n + z h
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)                  // h(t) replaces h(t-1) in place
-                        *reinterpret_cast<float4 *>(hp_row + (((c * 4 + q) ^ sw) << 4)) =
+                    for (int q = 0; q < 2; ++q)                  // h(t) replaces h(t-1) in place
+                        *reinterpret_cast<float4 *>(hp_row + (((ch + q) ^ sw) << 4)) =
                             make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
-                    *reinterpret_cast<uint4 *>(hb_row + (((half * 4 + c * 2) ^ sw) << 4)) = pack_bf16x8(hn);
-                    *reinterpret_cast<uint4 *>(hb_row + (((half * 4 + c * 2 + 1) ^ sw) << 4)) = pack_bf16x8(hn + 8);
+                    *reinterpret_cast<uint4 *>(hb_row + (((part * 2 + c) ^ sw) << 4)) = pack_bf16x8(hn);
+                    if (te == 0) KTRACE(it * 48 + 9 + c * 2);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 if (te == 0) KTRACE(it * 48 + 6);
                 mbar_arrive_cluster(empty_leader[ab]);           // accumulator buffer back to the MMA issuer before the stores
                 fence_proxy_async();                             // my smem writes -> visible to the TMA engine
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                asm volatile("bar.sync 3, %0;" ::"n"(kTcEpiThreads) : "memory");
                 if (te == 0) {
                     const int r0 = m * kTcPairM + (int) rank * kTcBlockM, u0 = n * kGruUnits;
-                    tma_store_2d(&map_hn, s_hp, u0, r0);
-                    tma_store_2d(&map_hn, s_hp + Cfg::kEpiF32Bytes / 2, u0 + 32, r0);
+                    tma_store_2d(&map_hn, hp_buf, u0, r0);
+                    tma_store_2d(&map_hn, hp_buf + Cfg::kEpiF32Bytes / 2, u0 + 32, r0);
                     tma_store_2d(&map_hb, s_hb, u0, r0);
                     bulk_commit();
-                    const int next = tile + num_clusters;
-                    if (next < num_tiles) {                      // next tile's h(t-1) may overwrite s_hp once the stores have read it
-                        bulk_wait_read();
-                        const int m1 = (next / ctiles_n) * kPM + qm, n1 = (next % ctiles_n) * kPN + qn;
-                        mbar_expect_tx(hp_full, Cfg::kEpiF32Bytes);
-                        tma_load_2d_local(&map_hp, hp_full, s_hp, n1 * kGruUnits, m1 * kTcPairM + (int) rank * kTcBlockM);
-                        tma_load_2d_local(&map_hp, hp_full, s_hp + Cfg::kEpiF32Bytes / 2, n1 * kGruUnits + 32, m1 * kTcPairM + (int) rank * kTcBlockM);
-                    } else {
-                        bulk_wait_all();                         // smem must outlive the last stores
-                    }
+                    if (tile + num_clusters >= num_tiles) bulk_wait_all();   // smem must outlive the last stores
                     KTRACE(it * 48 + 7);
                 }
-                continue;
             } else {
-                // my 64 of the tile's 128 outputs: bias + activation, staged in 128B-swizzled smem boxes, stored by TMA
-                const int sw = row_in_cta & 7;
+                // my 32 of the tile's 128 outputs: bias + activation, staged in 128B-swizzled smem boxes, stored by TMA
+                if (te == 0) bulk_wait_read();                   // previous tile's stores have read the staging buffer
+                asm volatile("bar.sync 2, %0;" ::"n"(kTcEpiThreads) : "memory");
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int cc = half * 64 + c * 16;
-                    float acc[16];
-                    tmem_ld16(t0 + cc, acc);
+                    const int cc = part * 32 + c * 8;
+                    float acc[8];
+                    tmem_ld8(t0 + cc, acc);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         const float v = acc[i] + sb[cc + i];
                         acc[i] = MODE == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
                     }
-                    if (MODE == kTcEnc) {        // bf16: box `half` = [128 rows][64 bf16], my chunk pair 2c, 2c+1
-                        uint8_t *rowp = s_hb + half * (kTcBlockM * 128) + row_in_cta * 128;
-                        *reinterpret_cast<uint4 *>(rowp + (((2 * c) ^ sw) << 4)) = pack_bf16x8(acc);
-                        *reinterpret_cast<uint4 *>(rowp + (((2 * c + 1) ^ sw) << 4)) = pack_bf16x8(acc + 8);
-                    } else {                     // fp32: box 2 * half + c / 2 = [128 rows][32 floats], my chunks 4 (c & 1) + q
-                        uint8_t *rowp = s_hp + (2 * half + (c >> 1)) * (kTcBlockM * 128) + row_in_cta * 128;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4 *>(rowp + (((4 * (c & 1) + q) ^ sw) << 4)) =
-                                make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    if (MODE == kTcEnc) {        // bf16 boxes [128 rows][64 bf16]: box part / 2, chunk (part & 1) * 4 + c
+                        uint8_t *rowp = s_hb + (part >> 1) * (kTcBlockM * 128) + row_in_cta * 128;
+                        *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + c) ^ sw) << 4)) = pack_bf16x8(acc);
+                    } else {                     // fp32 boxes [128 rows][32 floats]: box part, chunks 2c, 2c + 1
+                        uint8_t *rowp = s_hp + part * (kTcBlockM * 128) + row_in_cta * 128;
+                        *reinterpret_cast<float4 *>(rowp + (((2 * c) ^ sw) << 4)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        *reinterpret_cast<float4 *>(rowp + (((2 * c + 1) ^ sw) << 4)) = make_float4(acc[4], acc[5], acc[6], acc[7]);
                     }
                 }
                 tc_fence_before();
                 if (te == 0) KTRACE(it * 48 + 6);
                 mbar_arrive_cluster(empty_leader[ab]);
                 fence_proxy_async();
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                asm volatile("bar.sync 3, %0;" ::"n"(kTcEpiThreads) : "memory");
                 if (te == 0) {
                     const int r0 = m * kTcPairM + (int) rank * kTcBlockM, c0 = n * Cfg::kLinN;
                     if (MODE == kTcEnc) {
@@ -518,8 +560,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                         for (int b4 = 0; b4 < 4; ++b4) tma_store_2d(&map_hn, s_hp + b4 * (kTcBlockM * 128), c0 + 32 * b4, r0);
                     }
                     bulk_commit();
-                    if (tile + num_clusters < num_tiles) bulk_wait_read();   // staging is rewritten by my next tile
-                    else bulk_wait_all();
+                    if (tile + num_clusters >= num_tiles) bulk_wait_all();
                     KTRACE(it * 48 + 7);
                 }
             }
@@ -528,7 +569,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if (threadIdx.x == 0) KTRACE(502);
     tc_fence_before();
     cluster_sync_all();      // the peer's smem / TMEM are read and written by the leader's MMAs: leave together
-    if (warp == 1) {
+    if (warp == 2) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, 2 * kTcAccCols);
     }

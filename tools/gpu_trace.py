@@ -19,6 +19,7 @@ for cta in range(2):
         if t[b+4] == 0 and t[b+0] == 0: continue
         r = lambda x: (x - t0) if x else -1
         print(f" tile {it}: prod first {r(t[b+0])} last {r(t[b+1])} | mma buf_free {r(t[b+2])} done_issue {r(t[b+3])} | epi ready {r(t[b+4])} acc_full {r(t[b+5])} pre_arrive {r(t[b+6])} arrived {r(t[b+7])}")
+        print("    epi detail: chunk0 loaded", r(t[b+8]), "chunk0 done", r(t[b+9]), "chunk1 loaded", r(t[b+10]), "chunk1 done", r(t[b+11]))
         print("    prod slot-free per kb:", [int(r(x)) for x in t[b+16:b+32]])
         print("    mma  data-full per kb:", [int(r(x)) for x in t[b+32:b+48]])
 
