@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--workload", default="cfg4_8192_per_gpu_bf16", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
     ap.add_argument("--ring-frames", type=int, default=64, help="distinct input frames per stream kept in HBM")
-    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--e2e-steps", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -260,19 +260,29 @@ def main():
     prof = eng.profile_read()
     eng.profile(False)
 
-    # ---- end to end through the public API with pinned host buffers (H2D + compute + D2H every step)
-    e2e_steps = max(3, args.e2e_steps)
-    h_in = torch.from_numpy(host_pcm[:, :8, :].copy()).pin_memory()
-    h_frames = [h_in[:, t, :].contiguous().pin_memory() for t in range(8)]
-    h_out = torch.empty_like(h_frames[0]).pin_memory()
-    for i in range(3):
-        eng.process(h_frames[i % 8], out=h_out)
+    # ---- end to end through the public API with pinned HOST buffers: one call carries e2e_steps frames of every stream;
+    # inside it every step's 256-sample frames go host -> device and its enhanced frames device -> host (chunked, copies
+    # overlapped with compute by the library's ingest path).  Timed by wall clock around the synchronous call.
+    e2e_steps = max(8, args.e2e_steps)
+    e2e_ring = min(e2e_steps, ring)
+    h_in = torch.from_numpy(np.ascontiguousarray(host_pcm[:, :e2e_ring, :])).pin_memory()
+    if e2e_ring < e2e_steps:
+        h_in = h_in.repeat(1, (e2e_steps + e2e_ring - 1) // e2e_ring, 1)[:, :e2e_steps, :].contiguous().pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    eng.process(h_in[:, :8, :].contiguous().pin_memory(), out=torch.empty_like(h_in[:, :8, :]).contiguous().pin_memory())   # warm-up (allocates staging)
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        eng.process(h_frames[i % 8], out=h_out)                   # synchronous: returns when h_out is valid
+    eng.process(h_in, out=h_out)                                  # synchronous: returns when h_out is valid
     torch.cuda.synchronize(dev)
     e2e_s_local = time.perf_counter() - t0
+    # the same thing one step per call (the latency-bound way to drive the API), for reference
+    h1_in = h_in[:, 0, :].contiguous().pin_memory()
+    h1_out = torch.empty_like(h1_in).pin_memory()
+    eng.process(h1_in, out=h1_out)
+    t0 = time.perf_counter()
+    for i in range(20):
+        eng.process(h1_in, out=h1_out)
+    e2e_single_call_fps = streams * 20 / (time.perf_counter() - t0)
 
     # ---- reduce over ranks: SUM of units, MAX of time
     def reduce(v, op):
@@ -344,7 +354,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": streams * FRAME * 2,
                     "d2h_bytes_per_step": streams * FRAME * 2, "steps": e2e_steps,
-                    "api": "koala_b200.BatchKoala.process(pinned host tensor) -> pv_koala_batch_process"},
+                    "api": "koala_b200.BatchKoala.process(pinned host tensor [B][steps][256]) -> pv_koala_batch_process, one call",
+                    "one_step_per_call_value_rank0": e2e_single_call_fps},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

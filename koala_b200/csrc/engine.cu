@@ -98,6 +98,9 @@ Status load_model_file(const char *path, ModelHost *out, std::vector<std::string
 }
 
 // ------------------------------------------------------------------------------------------------ engine
+constexpr int kHostRing = 3;           // device staging buffers of the host ingest path
+constexpr int kHostChunkFrames = 8;    // frames per staged chunk
+
 struct Engine::Impl {
     cudaStream_t stream = nullptr;
     int H = 0, L = 0, num_sms = 148;
@@ -117,8 +120,10 @@ struct Engine::Impl {
     void *e = nullptr;           // fp32 | bf16 [Bp][H]
     float *mask = nullptr;       // [Bp][256]
     // staging for host-buffer calls
-    int16_t *d_in = nullptr, *d_out = nullptr;
+    int16_t *d_in[kHostRing] = {}, *d_out[kHostRing] = {};   // [B][staging_frames][256] each
     size_t staging_frames = 0;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[kHostRing] = {}, ev_comp[kHostRing] = {}, ev_out[kHostRing] = {};
     TcPlan *tc = nullptr;        // tensor maps + packed weights of the tcgen05 path
     KernelProfiler *prof = nullptr;
     std::vector<void *> allocs;
@@ -249,8 +254,15 @@ Engine::~Engine() {
     if (p_->tc) tc_plan_destroy(p_->tc);
     delete p_->prof;
     for (void *a : p_->allocs) cudaFree(a);
-    if (p_->d_in) cudaFree(p_->d_in);
-    if (p_->d_out) cudaFree(p_->d_out);
+    for (int i = 0; i < kHostRing; i++) {
+        if (p_->d_in[i]) cudaFree(p_->d_in[i]);
+        if (p_->d_out[i]) cudaFree(p_->d_out[i]);
+        if (p_->ev_in[i]) cudaEventDestroy(p_->ev_in[i]);
+        if (p_->ev_comp[i]) cudaEventDestroy(p_->ev_comp[i]);
+        if (p_->ev_out[i]) cudaEventDestroy(p_->ev_out[i]);
+    }
+    if (p_->copy_in) cudaStreamDestroy(p_->copy_in);
+    if (p_->copy_out) cudaStreamDestroy(p_->copy_out);
     if (p_->stream) cudaStreamDestroy(p_->stream);
     delete p_;
 }
@@ -307,6 +319,10 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     return kSuccess;
 }
 
+// Host ingest path: the caller's [B][frames][256] host buffers are cut into chunks of up to
+// kHostChunkFrames frames; chunk c+1 travels host -> device and chunk c-1 device -> host on their own streams while chunk c
+// is being processed, through a ring of three device staging buffers.  With pinned host memory the copies are true DMA
+// and the call is compute-bound from the second chunk on; pageable memory still works (the copies just serialise).
 Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::vector<std::string> *errors) {
     if (!pcm || !out || frames < 0) {
         if (errors) errors->push_back("PCM buffers must be non-NULL.");
@@ -315,20 +331,51 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
     if (frames == 0) return kSuccess;
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
-    if ((size_t) frames > p->staging_frames) {
-        if (p->d_in) cudaFree(p->d_in);
-        if (p->d_out) cudaFree(p->d_out);
-        p->d_in = p->d_out = nullptr;
+    const int Tc = frames < kHostChunkFrames ? frames : kHostChunkFrames;
+    if ((size_t) Tc > p->staging_frames) {
+        for (int i = 0; i < kHostRing; i++) {
+            if (p->d_in[i]) cudaFree(p->d_in[i]);
+            if (p->d_out[i]) cudaFree(p->d_out[i]);
+            p->d_in[i] = p->d_out[i] = nullptr;
+        }
         p->staging_frames = 0;
-        KCHECK(cudaMalloc((void **) &p->d_in, (size_t) n_ * frames * kFrame * sizeof(int16_t)));
-        KCHECK(cudaMalloc((void **) &p->d_out, (size_t) n_ * frames * kFrame * sizeof(int16_t)));
-        p->staging_frames = frames;
+        for (int i = 0; i < kHostRing; i++) {
+            KCHECK(cudaMalloc((void **) &p->d_in[i], (size_t) n_ * Tc * kFrame * sizeof(int16_t)));
+            KCHECK(cudaMalloc((void **) &p->d_out[i], (size_t) n_ * Tc * kFrame * sizeof(int16_t)));
+        }
+        p->staging_frames = Tc;
     }
-    const size_t bytes = (size_t) n_ * frames * kFrame * sizeof(int16_t);
-    KCHECK(cudaMemcpyAsync(p->d_in, pcm, bytes, cudaMemcpyHostToDevice, p->stream));
-    Status st = process_device(p->d_in, p->d_out, frames, (long long) frames * kFrame, p->stream, errors);
-    if (st != kSuccess) return st;
-    KCHECK(cudaMemcpyAsync(out, p->d_out, bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (!p->copy_in) {
+        KCHECK(cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking));
+        KCHECK(cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < kHostRing; i++) {
+            KCHECK(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+            KCHECK(cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
+            KCHECK(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t dpitch = (size_t) p->staging_frames * kFrame * sizeof(int16_t);   // device staging: [B][Tc][256]
+    const size_t hpitch = (size_t) frames * kFrame * sizeof(int16_t);              // host: [B][frames][256]
+    const int chunks = (frames + Tc - 1) / Tc;
+    for (int c = 0; c < chunks; c++) {
+        const int buf = c % kHostRing, t0 = c * Tc, tc = frames - t0 < Tc ? frames - t0 : Tc;
+        const size_t width = (size_t) tc * kFrame * sizeof(int16_t);
+        // host -> device once the compute that last used this staging buffer is done
+        if (c >= kHostRing) KCHECK(cudaStreamWaitEvent(p->copy_in, p->ev_comp[buf], 0));
+        KCHECK(cudaMemcpy2DAsync(p->d_in[buf], dpitch, pcm + (size_t) t0 * kFrame, hpitch, width, n_, cudaMemcpyHostToDevice, p->copy_in));
+        KCHECK(cudaEventRecord(p->ev_in[buf], p->copy_in));
+        // compute once the input has landed and the previous contents of the output staging buffer have left
+        KCHECK(cudaStreamWaitEvent(p->stream, p->ev_in[buf], 0));
+        if (c >= kHostRing) KCHECK(cudaStreamWaitEvent(p->stream, p->ev_out[buf], 0));
+        Status st = process_device(p->d_in[buf], p->d_out[buf], tc, (long long) p->staging_frames * kFrame, p->stream, errors);
+        if (st != kSuccess) return st;
+        KCHECK(cudaEventRecord(p->ev_comp[buf], p->stream));
+        // device -> host
+        KCHECK(cudaStreamWaitEvent(p->copy_out, p->ev_comp[buf], 0));
+        KCHECK(cudaMemcpy2DAsync(out + (size_t) t0 * kFrame, hpitch, p->d_out[buf], dpitch, width, n_, cudaMemcpyDeviceToHost, p->copy_out));
+        KCHECK(cudaEventRecord(p->ev_out[buf], p->copy_out));
+    }
+    KCHECK(cudaStreamSynchronize(p->copy_out));
     KCHECK(cudaStreamSynchronize(p->stream));
     return kSuccess;
 }
