@@ -42,6 +42,11 @@ STATE_BYTES = 512 + 1024 + LAYERS * HIDDEN * 4                                  
 BYTES_PER_FRAME = 1024 + 2 * STATE_BYTES
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
+# of this workload (profiles/r01_step_ncu_full_selected_metrics.csv); other workloads have no capture -> null
+NCU_DRAM_TRAFFIC_BYTES = {"cfg4_8192_per_gpu_bf16": 37.0e6 + 1.3e6}
+
+
 def synth_pcm(n_streams: int, n_frames: int, seed: int) -> np.ndarray:
     """SURVEY.md section 8d synthetic input: half band-limited noise (rms 760 LSB), half speech-like harmonic stack
     (rms 2030 LSB, 4 Hz syllabic AM) + noise.  Built from a small pool and tiled so set-up stays fast."""
@@ -75,7 +80,8 @@ def bench_model_path() -> str:
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 100 ms during the timed region."""
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 20 ms; started before warm-up so that samples exist
+    for short timed regions, and reduced over the samples that fall inside the timed window."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -84,7 +90,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -92,17 +98,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
+        rows = self.rows
+        if t_begin is not None and rows:
+            inside = [r for r in rows if t_begin - 0.03 <= r[0] <= t_end + 0.03]
+            rows = inside if inside else [min(rows, key=lambda r: abs(r[0] - 0.5 * (t_begin + t_end)))]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for _, r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -175,7 +190,7 @@ def run_reference(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4_8192_per_gpu_bf16", choices=sorted(WORKLOADS))
@@ -235,20 +250,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.wait_first()
     launches0 = eng.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     ev0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.time())
     ms_local = ev0.elapsed_time(ev1)
     launches_local = eng.kernel_launches - launches0
 
@@ -316,7 +333,8 @@ def main():
             peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
             achieved = GRU_FLOPS_PER_STREAM * streams / (gru_ms / max(gru_n, 1) * 1e-3) / 1e12 if gru_n else None
             roofline = {"bound": "tensor", "kernel": "tc_masknet_kernel<GRU> (one GRU layer, all streams)", "achieved": achieved,
-                        "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                        "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                        "traffic": NCU_DRAM_TRAFFIC_BYTES.get(args.workload) if not args.streams else None,
                         "peak_source": peak_src, "avg_launch_ms": gru_ms / max(gru_n, 1),
                         "algorithmic_flops_per_launch": GRU_FLOPS_PER_STREAM * streams}
         else:
