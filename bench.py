@@ -231,7 +231,9 @@ def main():
 
     ring = args.ring_frames
     host_pcm = synth_pcm(streams, ring, seed=0x4B4F414C + rank)
-    d_in = torch.from_numpy(host_pcm).to(dev)                     # [B][ring][256] resident in HBM
+    # resident in HBM, time-major [ring][B][256]: each step's frames are one contiguous [B][256] block, exactly what a
+    # caller of the one-frame-per-call API hands over (stream stride 256)
+    d_in = torch.from_numpy(np.ascontiguousarray(host_pcm.transpose(1, 0, 2))).to(dev)
     d_out = torch.empty_like(d_in)
     stream = torch.cuda.Stream(dev)                                # the launching stream: kernels AND timing events go here
     torch.cuda.set_stream(stream)
@@ -239,9 +241,9 @@ def main():
     from ctypes import c_void_p
 
     def step(i):
-        t = i % ring                                              # frame t of every stream: base + s*ring*256 + t*256
-        rc = lib.pv_koala_batch_process_async(handle, d_in.data_ptr() + t * FRAME * 2, d_out.data_ptr() + t * FRAME * 2,
-                                              1, ring * FRAME, c_void_p(stream.cuda_stream))
+        off = (i % ring) * streams * FRAME * 2                     # ring slot = a [B][256] block: frame of stream s at + s*256
+        rc = lib.pv_koala_batch_process_async(handle, d_in.data_ptr() + off, d_out.data_ptr() + off, 1, FRAME,
+                                              c_void_p(stream.cuda_stream))
         if rc != 0:
             raise RuntimeError(f"pv_koala_batch_process_async failed with status {rc}")
 

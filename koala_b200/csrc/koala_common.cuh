@@ -187,7 +187,7 @@ __device__ __forceinline__ constexpr int partner_reg(int j) {
 __device__ __forceinline__ constexpr int rev3c(int j) { return ((j & 1) << 2) | (j & 2) | ((j >> 2) & 1); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// mbarrier + 1-D bulk copy (TMA engine, no tensor map) used to stage lookup tables into shared memory
+// mbarrier helpers shared by the TMA / tcgen05 pipelines
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -214,13 +214,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // accurate-enough transcendental forms shared by every epilogue (abs error ~1e-7, see SPEC.md "numerics")
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) {

@@ -6,13 +6,14 @@
 // per tile, each SM loads its own 128 activation rows and HALF of the weight rows) accumulating fp32 in TMEM, gates /
 // state update / activation fused into the epilogue that reads TMEM back with tcgen05.ld.
 //
-// Why CTA pairs: the first version (cta_group::1, 128 x 192 tiles) was bound by the SM's L2 port -- 40 KB of operands per
-// 64-wide k-block against ~400 cycles of MMA (profiles/r01_step_summary.md).  Sharing the weight tile between the two
-// SMs of a pair cuts that to 28 KB.
+// Why CTA pairs and clusters: the first version (cta_group::1, 128 x 192 tiles) needed 40 KB of operands per 64-wide
+// k-block against ~400 cycles of MMA; sharing the weight tile between the two SMs of a pair cuts that to 28 KB, and the GRU
+// kernel additionally multicasts each activation tile to the two pairs of a 4-CTA cluster that work on neighbouring unit
+// tiles (20 KB of L2 reads per CTA per k-block).  Measurements behind every choice: profiles/r01_step_summary.md.
 //
-// One persistent CTA pair per 2 SMs, 21 warps per CTA: warps 0,1 / 3,4 = TMA producers (activations / weights, even / odd
-// k-blocks), warp 2 = TMEM allocator + (leader CTA only) MMA issuer, warps 5-20 = epilogue (four warps per TMEM lane quarter).  Two accumulator buffers of
-// 256 TMEM columns let the epilogue of tile i overlap the MMAs of tile i+1.
+// Persistent clusters, 21 warps per CTA: warps 0,1 / 3,4 = TMA producers (activations / weights x even / odd k-blocks),
+// warp 2 = TMEM allocator + (leader CTA only) MMA issuer, warps 5-20 = epilogue (four warps per TMEM lane quarter).
+// Two accumulator buffers of 256 TMEM columns let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // GRU tile = 256 streams x 64 hidden units.  TMEM columns per buffer: [n_x 0..63 | r 64..127 | z 128..191 | n_h 192..255].
 //   x-part (K = H): one N=192 MMA per k-step, packed W_ih rows ordered n|r|z, D column base   0 -> n_x, r, z
@@ -79,7 +80,6 @@ struct TcArgs {
     __nv_bfloat16 *out_bf16;    // enc: e [Bp][H]; GRU: bf16 copy of h_next
     float *out_f32;             // dec: mask [Bp][256]
     long long *trace;           // optional clock64() timeline of CTAs 0 and 1 (KOALA_TC_TRACE=1), else nullptr
-    int debug_flags;            // timing experiments only (KOALA_TC_DEBUG): 1 = skip the epilogue's global loads / stores
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -173,16 +173,6 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -206,14 +196,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// clears 16 consecutive TMEM columns of this thread's lane
-__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
-    const uint32_t z = 0;
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
-        "r"(z)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows at 128 B pitch, 8-row groups at 1024 B (SBO), version 1 (sm_100), layout 2
@@ -604,7 +586,6 @@ struct TcPlan {
     int num_sms = 0;
     long long *trace = nullptr;   // 2 x 512 clock64 slots, filled by one kernel: KOALA_TC_TRACE=1 GRU layer 0, 2 decoder, 3 encoder
     int trace_kernel = 0;
-    int debug_flags = 0;
     __nv_bfloat16 *wih_p[kMaxLayers] = {}, *whh_p[kMaxLayers] = {};
     CUtensorMap a_feat, a_hb_dec[2];                    // linear kernels: activation operands [Bp][K], box 64 x 128
     CUtensorMap a_e, a_hb[2][kMaxLayers];               // GRU kernel: box 64 x (128 / PN)
@@ -722,8 +703,6 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
     p->max_clusters[kTcEnc] = occupancy(tc_masknet_kernel<kTcEnc>, TcCfg<kTcEnc>::kCluster, TcCfg<kTcEnc>::kSmemBytes);
     p->max_clusters[kTcGru] = occupancy(tc_masknet_kernel<kTcGru>, TcCfg<kTcGru>::kCluster, TcCfg<kTcGru>::kSmemBytes);
     p->max_clusters[kTcDec] = occupancy(tc_masknet_kernel<kTcDec>, TcCfg<kTcDec>::kCluster, TcCfg<kTcDec>::kSmemBytes);
-    const char *dbg = getenv("KOALA_TC_DEBUG");
-    p->debug_flags = dbg ? atoi(dbg) : 0;
     const char *tr = getenv("KOALA_TC_TRACE");
     if (tr && *tr >= '1' && *tr <= '3') {
         p->trace_kernel = *tr - '0';
@@ -761,7 +740,6 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.bias0 = m.bih[l]; a.bias1 = m.bhh[l];
         a.h_prev = m.h[cur] + l * LBH; a.h_next = m.h[nxt] + l * LBH; a.out_bf16 = m.hb[nxt] + l * LBH;
         a.trace = (l == 0 && p->trace_kernel == 1) ? p->trace : nullptr;
-        a.debug_flags = p->debug_flags;
         const CUtensorMap &ax = l == 0 ? p->a_e : p->a_hb[nxt][l - 1];
         if (prof) prof->begin(kKernGru, st);
         tc_masknet_kernel<kTcGru><<<grid(kTcGru, C::kCluster, (mt / C::kPM) * (a.num_n_tiles / C::kPN)), kTcThreads, C::kSmemBytes, st>>>(
