@@ -9,5 +9,6 @@ from ._factory import *    # noqa: F401,F403
 from ._koala import *      # noqa: F401,F403
 from ._util import *       # noqa: F401,F403
 from .sharding import *    # noqa: F401,F403
+from .files import *       # noqa: F401,F403
 
 __version__ = "1.0.0"
