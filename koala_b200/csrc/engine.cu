@@ -291,31 +291,31 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
         if (precision_ == kFp32) {
             float *feat = (float *) p->feat, *e = (float *) p->e;
             if (prof) prof->begin(kKernFrontend, st);
-            frontend_kernel<float><<<stft_grid, kStftWarps * 32, 0, st>>>(v, B, p->tail, p->spec, feat, p->tables);
+            launch_pdl(false, frontend_kernel<float>, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->tail, p->spec, feat, p->tables);
             if (prof) { prof->end(st); prof->begin(kKernEnc, st); }
-            linear_fp32_kernel<kActRelu><<<dim3(Bp / kF32Bm, H / 64), 256, 0, st>>>(feat, p->enc_w, p->enc_b, e, kBins, H);
+            launch_pdl(false, linear_fp32_kernel<kActRelu>, dim3(Bp / kF32Bm, H / 64), dim3(256), 0, st, feat, p->enc_w, p->enc_b, e, kBins, H);
             if (prof) prof->end(st);
             const float *x = e;
             for (int l = 0; l < L; l++) {
                 if (prof) prof->begin(kKernGru, st);
-                gru_fp32_kernel<<<dim3(Bp / kF32Bm, H / 16), 256, 0, st>>>(x, p->h[cur] + l * LBH, p->h[nxt] + l * LBH,
+                launch_pdl(false, gru_fp32_kernel, dim3(Bp / kF32Bm, H / 16), dim3(256), 0, st, x, p->h[cur] + l * LBH, p->h[nxt] + l * LBH,
                                                                             p->wih[l], p->whh[l], p->bih[l], p->bhh[l], H);
                 if (prof) prof->end(st);
                 x = p->h[nxt] + l * LBH;
             }
             if (prof) prof->begin(kKernDec, st);
-            linear_fp32_kernel<kActSigmoid><<<dim3(Bp / kF32Bm, kBins / 64), 256, 0, st>>>(x, p->dec_w, p->dec_b, p->mask, H, kBins);
+            launch_pdl(false, linear_fp32_kernel<kActSigmoid>, dim3(Bp / kF32Bm, kBins / 64), dim3(256), 0, st, x, p->dec_w, p->dec_b, p->mask, H, kBins);
             if (prof) prof->end(st);
             launches_ += 3 + L;
         } else {
             if (prof) prof->begin(kKernFrontend, st);
-            frontend_kernel<__nv_bfloat16><<<stft_grid, kStftWarps * 32, 0, st>>>(v, B, p->tail, p->spec,
+            launch_pdl(true, frontend_kernel<__nv_bfloat16>, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->tail, p->spec,
                                                                                   (__nv_bfloat16 *) p->feat, p->tables);
             if (prof) prof->end(st);
             launches_ += 1 + tc_masknet_step(p->tc, cur, st, prof);
         }
         if (prof) prof->begin(kKernBackend, st);
-        backend_kernel<<<stft_grid, kStftWarps * 32, 0, st>>>(v, B, p->spec, p->mask, p->ola, p->tables);
+        launch_pdl(precision_ == kBf16, backend_kernel, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->spec, p->mask, p->ola, p->tables);
         if (prof) prof->end(st);
         launches_ += 1;
         p->parity = nxt;

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace koala {
 
@@ -214,6 +215,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// Programmatic dependent launch: every kernel of the step is launched with programmatic stream serialisation, calls
+// pdl_launch_dependents() first thing (so the next kernel's launch, CTA placement and prologue overlap this kernel) and
+// pdl_wait() before its first access to data produced by the previous kernel (blocks until that grid has fully finished).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Process-wide switch (KOALA_B200_PDL=0 turns it off).  The fp32 CUDA-core path launches without it: its many small grids ran
+// 50 % slower with every future kernel's CTAs parked on the SMs.
+static inline bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("KOALA_B200_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // accurate-enough transcendental forms shared by every epilogue (abs error ~1e-7, see SPEC.md "numerics")
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) {

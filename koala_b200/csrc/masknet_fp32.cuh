@@ -40,6 +40,8 @@ linear_fp32_kernel(const float *__restrict__ A, const __nv_bfloat16 *__restrict_
                    float *__restrict__ out, int K, int N) {
     __shared__ __align__(16) float As[kF32Bk][kF32Bm + kF32Pad];
     __shared__ __align__(16) float Ws[kF32Bk][64 + kF32Pad];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.x * kF32Bm, n0 = blockIdx.y * 64;
     float acc[4][4] = {};
@@ -88,6 +90,8 @@ gru_fp32_kernel(const float *__restrict__ x, const float *__restrict__ h_prev, f
                 const float *__restrict__ bih, const float *__restrict__ bhh, int H) {
     __shared__ __align__(16) float As[kF32Bk][kF32Bm + kF32Pad];
     __shared__ __align__(16) float Ws[kF32Bk][48 + kF32Pad];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.x * kF32Bm, u0 = blockIdx.y * 16;
     float ar[4] = {}, az[4] = {}, anx[4] = {}, anh[4] = {};

@@ -252,6 +252,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     long long *trace = (args.trace != nullptr && blockIdx.x < 2) ? args.trace + blockIdx.x * 512 : nullptr;
 #define KTRACE(slot) do { if (trace && (slot) < 512) trace[(slot)] = clock64(); } while (0)
     if (threadIdx.x == 0) KTRACE(500);
+    pdl_launch_dependents();
     const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
 
     if (warp == 0 && lane == 0) {
@@ -284,6 +285,7 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) KTRACE(501);
+    pdl_wait();      // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
     // cluster tiles: (num_m_tiles / PM) x (num_n_tiles / PN); every pair of the cluster walks the same sequence
     const int ctiles_n = args.num_n_tiles / kPN;
@@ -730,7 +732,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.bias0 = m.enc_b; a.out_bf16 = m.e;
         a.trace = p->trace_kernel == 3 ? p->trace : nullptr;
         if (prof) prof->begin(kKernEnc, st);
-        tc_masknet_kernel<kTcEnc><<<grid(kTcEnc, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_feat, p->a_feat, p->b_enc, p->b_enc, p->a_feat, p->e128, p->a_feat, a);
+        launch_pdl(true, tc_masknet_kernel<kTcEnc>, dim3((unsigned) grid(kTcEnc, C::kCluster, mt * a.num_n_tiles)), dim3(kTcThreads), (size_t) C::kSmemBytes, st, p->a_feat, p->a_feat, p->b_enc, p->b_enc, p->a_feat, p->e128, p->a_feat, a);
         if (prof) prof->end(st);
     }
     for (int l = 0; l < m.L; l++) {
@@ -742,8 +744,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.trace = (l == 0 && p->trace_kernel == 1) ? p->trace : nullptr;
         const CUtensorMap &ax = l == 0 ? p->a_e : p->a_hb[nxt][l - 1];
         if (prof) prof->begin(kKernGru, st);
-        tc_masknet_kernel<kTcGru><<<grid(kTcGru, C::kCluster, (mt / C::kPM) * (a.num_n_tiles / C::kPN)), kTcThreads, C::kSmemBytes, st>>>(
-            ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], p->hf[cur][l], p->hf[nxt][l], p->hb128[nxt][l], a);
+        launch_pdl(true, tc_masknet_kernel<kTcGru>, dim3((unsigned) grid(kTcGru, C::kCluster, (mt / C::kPM) * (a.num_n_tiles / C::kPN))), dim3(kTcThreads), (size_t) C::kSmemBytes, st, ax, p->a_hb[cur][l], p->b_ih[l], p->b_hh[l], p->hf[cur][l], p->hf[nxt][l], p->hb128[nxt][l], a);
         if (prof) prof->end(st);
     }
     {
@@ -753,7 +754,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.bias0 = m.dec_b; a.out_f32 = m.mask;
         a.trace = p->trace_kernel == 2 ? p->trace : nullptr;
         if (prof) prof->begin(kKernDec, st);
-        tc_masknet_kernel<kTcDec><<<grid(kTcDec, C::kCluster, mt * a.num_n_tiles), kTcThreads, C::kSmemBytes, st>>>(p->a_hb_dec[nxt], p->a_hb_dec[nxt], p->b_dec, p->b_dec, p->a_feat, p->mask_f32, p->a_feat, a);
+        launch_pdl(true, tc_masknet_kernel<kTcDec>, dim3((unsigned) grid(kTcDec, C::kCluster, mt * a.num_n_tiles)), dim3(kTcThreads), (size_t) C::kSmemBytes, st, p->a_hb_dec[nxt], p->a_hb_dec[nxt], p->b_dec, p->b_dec, p->a_feat, p->mask_f32, p->a_feat, a);
         if (prof) prof->end(st);
     }
     return 2 + m.L;

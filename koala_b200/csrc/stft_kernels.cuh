@@ -38,8 +38,10 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
     __shared__ __align__(16) int16_t s_frame[kStftWarps][kNfft];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     FftLane c;
-    load_fft_lane(c, lane_tab, lane);
+    load_fft_lane(c, lane_tab, lane);      // constants: may be read before the previous kernel has finished
+    pdl_wait();
     const uint32_t *fw = reinterpret_cast<const uint32_t *>(s_frame[warp]);
     const int a = rev5(lane);
     const int src_a = rev5((32 - a) & 31), src_b = 31 - lane;
@@ -101,8 +103,10 @@ __global__ void __launch_bounds__(kStftWarps * 32)
 backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const float *__restrict__ mask,
                float *__restrict__ ola, const float2 *__restrict__ lane_tab) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     FftLane c;
     load_fft_lane(c, lane_tab, lane);
+    pdl_wait();
     const int a = rev5(lane);
     const int src_a = rev5((32 - a) & 31), src_b = 31 - lane;
     constexpr float inv = 1.0f / 256.0f;
