@@ -218,3 +218,42 @@ def test_init_errors_on_gpu_box_match_reference_kat(library_path, shipped_model_
     assert list(e2.value.message_stack) == list(e.value.message_stack)      # repeatable
     with pytest.raises(kb.KoalaRuntimeError):
         kb.create(kb.ANY_ACCESS_KEY, model_path=shipped_model_path, device="gpu:99")
+
+
+def test_long_state_carry_does_not_drift(library_path, shipped_model_path, test_pcm, noise_pcm):
+    """BASELINE configs[4] in miniature: state carried over 1400 frames (22 s) in chunks of 64 frames per call; the CUDA
+    path must still sit within +-1 LSB of the oracle at the end, i.e. rounding differences do not accumulate in the
+    recurrent state (shipped weights, real speech + noise, bf16 path)."""
+    n, frames, chunk = 6, 1400, 64
+    mixed = np.clip(test_pcm.astype(np.int32) + noise_pcm.astype(np.int32), -32768, 32767).astype(np.int16)
+    src = [test_pcm, noise_pcm, mixed, test_pcm[5000:], noise_pcm[::-1].copy(), mixed[20000:]]
+    pcm = np.stack([np.resize(s, frames * 256) for s in src]).reshape(n, frames, 256)
+    eng = kb.BatchKoala(n, model_path=shipped_model_path, precision="bf16")
+    outs = [eng.process(np.ascontiguousarray(pcm[:, t:t + chunk])) for t in range(0, frames, chunk)]
+    out = np.concatenate(outs, axis=1)
+    ob, ref = run_oracle(shipped_model_path, "bf16", pcm)
+    diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= LSB_TOL, (diff.max(), np.argwhere(diff > LSB_TOL)[:5])
+    assert diff[:, -100:].max() <= LSB_TOL
+    for l in range(2):
+        h = eng.debug_read(f"h{l}", (n, 512), np.float32)
+        np.testing.assert_allclose(h, np.stack([ob.stream(s).h[l] for s in range(n)]), atol=2e-4)
+    eng.delete()
+
+
+def test_model_file_rejections_on_gpu_box(library_path, shipped_model_path, tmp_path):
+    """pv_koala_init validation order on a box with a GPU: device ok -> model file -> AccessKey."""
+    ref_like = str(tmp_path / "ref.pv")
+    open(ref_like, "wb").write(b"koala3.0.0\x01\x01\x01\x00\x00\x11" + bytes(200))
+    with pytest.raises(kb.KoalaInvalidArgumentError) as e:
+        kb.Koala(kb.ANY_ACCESS_KEY, ref_like, "gpu", library_path)
+    assert "library product is `koala_b200`" in e.value.message_stack[0]
+    blob = bytearray(open(shipped_model_path, "rb").read())
+    blob[5000] ^= 1
+    bad = str(tmp_path / "bad.kpv")
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises(kb.KoalaInvalidArgumentError) as e:
+        kb.Koala(kb.ANY_ACCESS_KEY, bad, "gpu", library_path)
+    assert "corrupt" in e.value.message_stack[0]
+    with pytest.raises(kb.KoalaInvalidArgumentError):                         # key is looked at after the model opened
+        kb.Koala("invalid", shipped_model_path, "gpu", library_path)
