@@ -235,9 +235,31 @@ def test_long_state_carry_does_not_drift(library_path, shipped_model_path, test_
     diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
     assert diff.max() <= LSB_TOL, (diff.max(), np.argwhere(diff > LSB_TOL)[:5])
     assert diff[:, -100:].max() <= LSB_TOL
+    # internal tensors after 1400 steps with trained weights: bf16 operand re-rounding (an operand on a rounding boundary
+    # may round the other way on the GPU) shows up as ~1e-3 in h and ~3e-4 in the mask; it does not grow with time and never
+    # reaches the int16 output (asserted above).  Measured: h 1.0e-3, mask 2.6e-4 abs (tools/gpu_long_carry.py).
+    mask = eng.debug_read("mask", (n, 256), np.float32)
+    np.testing.assert_allclose(mask, np.stack([ob.stream(s).last_mask for s in range(n)]), rtol=MASK_RTOL, atol=5e-4)
     for l in range(2):
         h = eng.debug_read(f"h{l}", (n, 512), np.float32)
-        np.testing.assert_allclose(h, np.stack([ob.stream(s).h[l] for s in range(n)]), atol=2e-4)
+        np.testing.assert_allclose(h, np.stack([ob.stream(s).h[l] for s in range(n)]), atol=3e-3)
+    eng.delete()
+
+
+def test_long_state_carry_fp32_is_tight(library_path, shipped_model_path, test_pcm, noise_pcm):
+    """Same run on the fp32 path: no operand re-rounding, so state and mask stay within 1e-4 / 1e-3 relative."""
+    n, frames = 3, 700
+    mixed = np.clip(test_pcm.astype(np.int32) + noise_pcm.astype(np.int32), -32768, 32767).astype(np.int16)
+    pcm = np.stack([np.resize(s, frames * 256) for s in (test_pcm, noise_pcm, mixed)]).reshape(n, frames, 256)
+    eng = kb.BatchKoala(n, model_path=shipped_model_path, precision="fp32")
+    out = eng.process(pcm)
+    ob, ref = run_oracle(shipped_model_path, "fp32", pcm)
+    assert np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= LSB_TOL
+    mask = eng.debug_read("mask", (n, 256), np.float32)
+    np.testing.assert_allclose(mask, np.stack([ob.stream(s).last_mask for s in range(n)]), rtol=MASK_RTOL, atol=1e-6)
+    for l in range(2):
+        h = eng.debug_read(f"h{l}", (n, 512), np.float32)
+        np.testing.assert_allclose(h, np.stack([ob.stream(s).h[l] for s in range(n)]), atol=1e-4)
     eng.delete()
 
 
