@@ -59,13 +59,16 @@ template <int MODE> struct TcCfg {
     static constexpr int kARowsPiece = kTcBlockM / kPN;                  // rows of A this CTA fetches (and multicasts)
     static constexpr int kBRowsPiece = kBRowsHalf / kPM;                 // rows of B this CTA fetches (and multicasts)
     static constexpr int kStageBytes = kTcABytes + kBRowsHalf * 128;     // 28 KB | 24 KB landing per CTA per stage
-    static constexpr int kStages = kGru ? 5 : 4;
+    static constexpr int kStages = kGru ? 6 : 4;
     // GRU only: the epilogue's h tile travels by TMA too (coalesced, off the LSU): fp32 h(t-1) lands in kEpiF32Bytes, is
     // replaced in place by h(t), and the bf16 copy of h(t) is staged in kEpiBf16Bytes; both leave through TMA stores
     // Linear kernels stage their [128 x 128] output tile the same way (encoder: bf16, decoder: fp32) and TMA-store it.
-    static constexpr int kEpiF32Bytes = kGru ? kTcBlockM * kGruUnits * 4 : (MODE == kTcDec ? kTcBlockM * kLinN * 4 : 0);    // 128B-swizzled boxes of 32 floats
-    static constexpr int kEpiBf16Bytes = kGru ? kTcBlockM * kGruUnits * 2 : (MODE == kTcEnc ? kTcBlockM * kLinN * 2 : 0);  // 128B-swizzled boxes of 64 bf16
-    static constexpr int kEpiF32Bufs = kGru ? 2 : 1;   // GRU: h(t-1) of the next tile lands while this tile's h(t) is being stored
+    // GRU: the state tile is handled in two passes of 32 units, each with its own staging buffers (fp32 box [128][32] that
+    // receives h(t-1) by TMA and is overwritten in place by h(t); bf16 box [128][32]) -- 48 KB instead of 80 KB for whole
+    // tiles, which pays for a 6th operand stage (the operand pipeline is the bottleneck, the epilogue has slack).
+    static constexpr int kEpiF32Bytes = kGru ? kTcBlockM * 32 * 4 : (MODE == kTcDec ? kTcBlockM * kLinN * 4 : 0);    // 128B-swizzled boxes of 32 floats
+    static constexpr int kEpiBf16Bytes = kGru ? 2 * kTcBlockM * 32 * 2 : (MODE == kTcEnc ? kTcBlockM * kLinN * 2 : 0);  // GRU: 2 plain boxes of 32 bf16; encoder: swizzled boxes of 64
+    static constexpr int kEpiF32Bufs = kGru ? 2 : 1;
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiF32Bufs * kEpiF32Bytes + kEpiBf16Bytes + kTcTailBytes;
 };
 
@@ -401,9 +404,11 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         const int sw = row_in_cta & 7;
         if (kGru && te == 0 && cluster_id < num_tiles) {
             const int m0 = (cluster_id / ctiles_n) * kPM + qm, n0 = (cluster_id % ctiles_n) * kPN + qn;
-            mbar_expect_tx(&hp_full[0], Cfg::kEpiF32Bytes);
-            tma_load_2d_local(&map_hp, &hp_full[0], s_hp, n0 * kGruUnits, m0 * kTcPairM + (int) rank * kTcBlockM);
-            tma_load_2d_local(&map_hp, &hp_full[0], s_hp + Cfg::kEpiF32Bytes / 2, n0 * kGruUnits + 32, m0 * kTcPairM + (int) rank * kTcBlockM);
+#pragma unroll
+            for (int p0 = 0; p0 < 2; ++p0) {
+                mbar_expect_tx(&hp_full[p0], Cfg::kEpiF32Bytes);
+                tma_load_2d_local(&map_hp, &hp_full[p0], s_hp + p0 * Cfg::kEpiF32Bytes, n0 * kGruUnits + 32 * p0, m0 * kTcPairM + (int) rank * kTcBlockM);
+            }
         }
         constexpr float kL2e = 1.4426950408889634f;
         int it = 0;
@@ -431,40 +436,24 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             if (te == 0) KTRACE(it * 48 + 5);
             const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (kGru) {
-                // fp32 tile buffers alternate per tile.  Before anything is written to shared memory again, the stores of the
-                // previous tile must have finished READING it (they were issued ~a whole mainloop ago); then the next tile's
-                // h(t-1) is requested into the other buffer so it is there when that tile's accumulator is.
-                uint8_t *hp_buf = s_hp + (it & 1) * Cfg::kEpiF32Bytes;
-                if (te == 0) {
-                    bulk_wait_read();
-                    const int next = tile + num_clusters;
-                    if (next < num_tiles) {
-                        uint8_t *nb = s_hp + ((it + 1) & 1) * Cfg::kEpiF32Bytes;
-                        uint64_t *nbar = &hp_full[(it + 1) & 1];
-                        const int m1 = (next / ctiles_n) * kPM + qm, n1 = (next % ctiles_n) * kPN + qn;
-                        mbar_expect_tx(nbar, Cfg::kEpiF32Bytes);
-                        tma_load_2d_local(&map_hp, nbar, nb, n1 * kGruUnits, m1 * kTcPairM + (int) rank * kTcBlockM);
-                        tma_load_2d_local(&map_hp, nbar, nb + Cfg::kEpiF32Bytes / 2, n1 * kGruUnits + 32, m1 * kTcPairM + (int) rank * kTcBlockM);
-                    }
-                }
-                asm volatile("bar.sync 2, %0;" ::"n"(kTcEpiThreads) : "memory");
-                mbar_wait(&hp_full[it & 1], (it >> 1) & 1);      // h(t-1) tile has landed
-                // 128B-swizzled tiles: 16-byte chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4).  My 16 units are half of
-                // an fp32 box row (4 chunks of 4 floats) and a quarter of the bf16 box row (2 chunks of 8)
-                uint8_t *hp_row = hp_buf + (part >> 1) * (Cfg::kEpiF32Bytes / 2) + row_in_cta * 128;
-                uint8_t *hb_row = s_hb + row_in_cta * 128;
+                // two passes of 32 units (pass c: units c * 32 .. c * 32 + 31 of the tile, 8 of them mine); pass buffers
+                // alternate, so h(t-1) of the next pass lands while this pass is computed and stored
+                const int r0 = m * kTcPairM + (int) rank * kTcBlockM, u0 = n * kGruUnits;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const int cu = part * 16 + c * 8;            // first of my 8 units inside the tile
+                    const int g = 2 * it + c;                    // running pass index: buffer c, phase it & 1
+                    uint8_t *f32_box = s_hp + c * Cfg::kEpiF32Bytes, *b16_box = s_hb + c * (Cfg::kEpiBf16Bytes / 2);
+                    uint8_t *f32_row = f32_box + row_in_cta * 128, *b16_row = b16_box + row_in_cta * 64;
+                    const int cu = c * 32 + part * 8;            // first of my 8 units inside the tile
                     float anx[8], ar[8], az[8], anh[8], hp[8], hn[8];
                     tmem_ld8(t0 + 0 + cu, anx);
                     tmem_ld8(t0 + 64 + cu, ar);
                     tmem_ld8(t0 + 128 + cu, az);
                     tmem_ld8(t0 + 192 + cu, anh);
-                    const int ch = (part & 1) * 4 + c * 2;       // first of my 2 fp32 chunks in the box row
+                    mbar_wait(&hp_full[c], it & 1);              // h(t-1) of this pass has landed
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const float4 t = *reinterpret_cast<const float4 *>(hp_row + (((ch + q) ^ sw) << 4));
+                        const float4 t = *reinterpret_cast<const float4 *>(f32_row + (((part * 2 + q) ^ sw) << 4));
                         hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
                     }
                     tmem_ld_wait();
@@ -483,28 +472,38 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                         const float ng = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(t * (2.0f * kL2e))), 1.0f);   // tanh(t)
                         hn[i] = fmaf(zg, hp[i] - ng, ng);        // (1 - z) n + z h
                     }
+                    if (c == 1) {                                // last TMEM access of this tile: hand the buffer back
+                        tmem_st_wait();
+                        tc_fence_before();
+                        if (te == 0) KTRACE(it * 48 + 6);
+                        mbar_arrive_cluster(empty_leader[ab]);
+                    }
 #pragma unroll
                     for (int q = 0; q < 2; ++q)                  // h(t) replaces h(t-1) in place
-                        *reinterpret_cast<float4 *>(hp_row + (((ch + q) ^ sw) << 4)) =
+                        *reinterpret_cast<float4 *>(f32_row + (((part * 2 + q) ^ sw) << 4)) =
                             make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
-                    *reinterpret_cast<uint4 *>(hb_row + (((part * 2 + c) ^ sw) << 4)) = pack_bf16x8(hn);
-                    if (te == 0) KTRACE(it * 48 + 9 + c * 2);
+                    *reinterpret_cast<uint4 *>(b16_row + part * 16) = pack_bf16x8(hn);
+                    fence_proxy_async();                         // my smem writes -> visible to the TMA engine
+                    asm volatile("bar.sync 2, %0;" ::"n"(kTcEpiThreads) : "memory");
+                    if (te == 0) {
+                        tma_store_2d(&map_hn, f32_box, u0 + c * 32, r0);
+                        tma_store_2d(&map_hb, b16_box, u0 + c * 32, r0);
+                        bulk_commit();
+                        // the other pass buffer was stored one pass ago: once that store has read it, the h(t-1) of pass g + 1
+                        // ... g + 1 uses buffer c ^ 1, whose last store is the group before this one
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        const int gn = g + 1, itn = gn >> 1, cn = gn & 1;
+                        const int tile_n = cluster_id + itn * num_clusters;
+                        if (gn >= 2 && tile_n < num_tiles) {     // passes 0 and 1 were requested before the loop
+                            const int m1 = (tile_n / ctiles_n) * kPM + qm, n1 = (tile_n % ctiles_n) * kPN + qn;
+                            mbar_expect_tx(&hp_full[cn], Cfg::kEpiF32Bytes);
+                            tma_load_2d_local(&map_hp, &hp_full[cn], s_hp + cn * Cfg::kEpiF32Bytes, n1 * kGruUnits + 32 * cn,
+                                              m1 * kTcPairM + (int) rank * kTcBlockM);
+                        }
+                        KTRACE(it * 48 + 9 + c * 2);
+                    }
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                if (te == 0) KTRACE(it * 48 + 6);
-                mbar_arrive_cluster(empty_leader[ab]);           // accumulator buffer back to the MMA issuer before the stores
-                fence_proxy_async();                             // my smem writes -> visible to the TMA engine
-                asm volatile("bar.sync 3, %0;" ::"n"(kTcEpiThreads) : "memory");
-                if (te == 0) {
-                    const int r0 = m * kTcPairM + (int) rank * kTcBlockM, u0 = n * kGruUnits;
-                    tma_store_2d(&map_hn, hp_buf, u0, r0);
-                    tma_store_2d(&map_hn, hp_buf + Cfg::kEpiF32Bytes / 2, u0 + 32, r0);
-                    tma_store_2d(&map_hb, s_hb, u0, r0);
-                    bulk_commit();
-                    if (tile + num_clusters >= num_tiles) bulk_wait_all();   // smem must outlive the last stores
-                    KTRACE(it * 48 + 7);
-                }
+                if (te == 0 && tile + num_clusters >= num_tiles) bulk_wait_all();   // smem must outlive the last stores
             } else {
                 // my 32 of the tile's 128 outputs: bias + activation, staged in 128B-swizzled smem boxes, stored by TMA
                 if (te == 0) bulk_wait_read();                   // previous tile's stores have read the staging buffer
@@ -594,7 +593,7 @@ struct TcPlan {
     CUtensorMap b_enc, b_dec, b_ih[kMaxLayers], b_hh[kMaxLayers];
     CUtensorMap e128, mask_f32;                         // linear epilogues: encoder output bf16 box 64 x 128, mask fp32 box 32 x 128
     CUtensorMap hf[2][kMaxLayers];                      // GRU epilogue: fp32 state [Bp][H], box 32 floats x 128 rows
-    CUtensorMap hb128[2][kMaxLayers];                   // GRU epilogue: bf16 state store, box 64 x 128
+    CUtensorMap hb128[2][kMaxLayers];                   // GRU epilogue: bf16 state store, box 32 x 128, no swizzle
     int max_clusters[3] = {0, 0, 0};                    // co-resident clusters per kernel (cudaOccupancyMaxActiveClusters)
 };
 
@@ -604,13 +603,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 // [rows][cols] row-major matrix, box = 128 bytes x box_rows, 128B swizzle; bf16 (64 elements per box row) or fp32 (32)
 static bool encode_2d(EncodeTiledFn fn, CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                      bool f32 = false) {
+                      bool f32 = false, bool plain32 = false) {
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {cols * (f32 ? 4 : 2)};
-    const cuuint32_t box[2] = {(cuuint32_t) (f32 ? 32 : kTcBlockK), box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t) ((f32 || plain32) ? 32 : kTcBlockK), box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, plain32 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -667,7 +666,7 @@ static bool tc_plan_create(const TcModel &m, TcPlan **out, std::string *why) {
         ok = ok && encode_2d(fn, &p->a_hb_dec[par], m.hb[par] + (size_t) (m.L - 1) * Bp * H, Bp, H, kTcBlockM);
         for (int l = 0; l < m.L; l++) {
             ok = ok && encode_2d(fn, &p->hf[par][l], m.h[par] + (size_t) l * Bp * H, Bp, H, kTcBlockM, true);
-            ok = ok && encode_2d(fn, &p->hb128[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, kTcBlockM);
+            ok = ok && encode_2d(fn, &p->hb128[par][l], m.hb[par] + (size_t) l * Bp * H, Bp, H, kTcBlockM, false, true);
         }
     }
     ok = ok && encode_2d(fn, &p->b_enc, m.enc_w, H, kBins, TcCfg<kTcEnc>::kBRowsHalf);
