@@ -104,7 +104,7 @@ constexpr int kHostChunkFrames = 8;    // frames per staged chunk
 
 struct Engine::Impl {
     cudaStream_t stream = nullptr;
-    int H = 0, L = 0, num_sms = 148, stft_per_warp = 2;
+    int H = 0, L = 0, num_sms = 148, stft_per_warp = 0;   // 0: derive from the stream count
     int parity = 0;   // h[parity] holds h(t-1)
     // model
     __nv_bfloat16 *enc_w = nullptr, *dec_w = nullptr, *wih[kMaxLayers] = {}, *whh[kMaxLayers] = {};
@@ -280,9 +280,10 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     cudaStream_t st = (cudaStream_t) stream_;
     const int B = n_, Bp = npad_, H = p->H, L = p->L;
     const size_t LBH = (size_t) Bp * H;
-    // STFT kernels: each warp walks `stft_per_warp` streams; more CTAs than fit at once, so the hardware scheduler balances
-    // the tail (a fixed persistent grid left SMs idle for ~30 % of these kernels: 3.46 streams per warp = 4 rounds for some)
-    const int stft_per_warp = p->stft_per_warp;
+    // STFT kernels: every warp walks the same number of streams, the smallest that keeps the whole grid resident
+    // (kStftCtasPerSm CTAs of kStftWarps warps per SM), so there is neither a second wave nor an uneven last round
+    const int resident_warps = p->num_sms * kStftCtasPerSm * kStftWarps;
+    const int stft_per_warp = p->stft_per_warp > 0 ? p->stft_per_warp : std::max(1, (B + resident_warps - 1) / resident_warps);
     const int stft_grid = std::max(1, (B + kStftWarps * stft_per_warp - 1) / (kStftWarps * stft_per_warp));
     KernelProfiler *prof = p->prof;
     for (int t = 0; t < frames; t++) {

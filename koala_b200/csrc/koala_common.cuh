@@ -92,20 +92,28 @@ __device__ __forceinline__ cpx shfl_c(cpx v, int src) {
 }
 __device__ __forceinline__ int rev5(int v) { return (int) (__brev((unsigned) v) >> 27); }
 
-// Per-lane constants of the warp FFT, held in registers for every stream a warp processes.  The host lays them out
-// lane-major (float2 [kLaneTabRows][32]) so that loading them is one coalesced 256-byte request per row and there is no
-// shared-memory twiddle traffic inside the stream loop (the first version read twiddles from shared memory with up to
-// 16-way bank conflicts and was LSU-bound: profiles/r01_step_summary.md).
+// Per-lane constants of the warp FFT.  The host lays them out lane-major (float2 [kLaneTabRows][32]): lane l's copy of
+// constant i is tab[i * 32 + l], so a row is one coalesced 256-byte request from global memory and a conflict-free access
+// from shared memory (the first version indexed twiddles by bin, with up to 16-way bank conflicts: profiles/r01_step_summary.md).
+// The twiddles of the butterfly stages (rows 0-10) are used by every stage and live in registers for all streams a warp
+// walks; the real-FFT split factors and the window (rows 11-26) are used once per frame and stay in shared memory, which
+// keeps the kernels under 72 registers = 28 resident warps per SM (these kernels are latency-bound: occupancy is speed).
 constexpr int kLaneTabRows = 27;
+constexpr int kLaneTabRegRows = 11;                               // t4, t2, t1, tx
+constexpr int kLaneTabSmemRows = kLaneTabRows - kLaneTabRegRows;  // tp[8], win[8]
 struct FftLane {
     float2 t4[4];    // span 128: W512^{2 (lane + 32 q)},  q = j & 3
     float2 t2[2];    // span  64: W512^{4 (lane + 32 q)},  q = j & 1
     float2 t1;       // span  32: W512^{8 lane}
     float2 tx[4];    // spans 16, 8, 4, 2 (lane exchange): W512^{(lane & (h-1)) * 256 / h}
-    float2 tp[8];    // real-FFT split: W512^{8 rev5(lane) + b}
-    float2 win[8];   // sqrt-Hann window pairs (w[2p], w[2p+1]), p = lane + 32 j
+    const float2 *sm;  // shared-memory rows of this lane: tp(b) = real-FFT split W512^{8 rev5(lane) + b}; win(j) = sqrt-Hann
+                       // window pair (w[2p], w[2p+1]), p = lane + 32 j
+    __device__ __forceinline__ float2 tp(int b) const { return sm[32 * b]; }
+    __device__ __forceinline__ float2 win(int j) const { return sm[32 * (8 + j)]; }
 };
-__device__ __forceinline__ void load_fft_lane(FftLane &c, const float2 *__restrict__ tab, int lane) {
+// s_tab: float2 [kLaneTabSmemRows * 32] of shared memory, filled by the whole CTA (ends with __syncthreads)
+__device__ __forceinline__ void load_fft_lane(FftLane &c, const float2 *__restrict__ tab, float2 *s_tab, int lane) {
+    for (int i = threadIdx.x; i < kLaneTabSmemRows * 32; i += blockDim.x) s_tab[i] = __ldg(tab + kLaneTabRegRows * 32 + i);
     const float2 *t = tab + lane;
 #pragma unroll
     for (int i = 0; i < 4; ++i) c.t4[i] = __ldg(t + 32 * i);
@@ -114,10 +122,8 @@ __device__ __forceinline__ void load_fft_lane(FftLane &c, const float2 *__restri
     c.t1 = __ldg(t + 32 * 6);
 #pragma unroll
     for (int i = 0; i < 4; ++i) c.tx[i] = __ldg(t + 32 * (7 + i));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) c.tp[i] = __ldg(t + 32 * (11 + i));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) c.win[i] = __ldg(t + 32 * (19 + i));
+    c.sm = s_tab + lane;
+    __syncthreads();
 }
 
 // One warp = one 256-point complex FFT.  Lane l, register j hold element p = l + 32 j.

@@ -38,7 +38,8 @@ constexpr int kTcBlockK = 64;                 // 64 bf16 = 128 bytes = one swizz
 constexpr int kTcABytes = kTcBlockM * 128;    // 16 KB
 constexpr int kTcEpiWarps = 16;               // 4 warps per TMEM lane quarter, each owning a quarter of the tile's columns
 constexpr int kTcEpiThreads = kTcEpiWarps * 32;
-constexpr int kTcThreads = 160 + kTcEpiThreads; // 2 TMA warps (A) + MMA warp + 2 TMA warps (B) + 16 epilogue warps
+constexpr int kTcStateWarp = 5 + kTcEpiWarps;    // GRU: moves the state tiles (h(t-1) in, h(t) out) by TMA for the epilogue warps
+constexpr int kTcThreads = 160 + kTcEpiThreads + 32; // 2 TMA warps (A) + MMA warp + 2 TMA warps (B) + 16 epilogue warps + state warp
 constexpr int kTcAccCols = 256;
 constexpr int kGruUnits = 64;                 // hidden units per GRU tile
 constexpr int kGruRows = 3 * kGruUnits;       // packed weight rows per tile (both CTAs together)
@@ -82,6 +83,7 @@ struct TcArgs {
     float *h_next;              // GRU fp32 state out [Bp][H]
     __nv_bfloat16 *out_bf16;    // enc: e [Bp][H]; GRU: bf16 copy of h_next
     float *out_f32;             // dec: mask [Bp][256]
+    const __nv_bfloat16 *a0, *a1;   // GRU: the two activation operands [Bp][H] (x, h(t-1) in bf16), for L2 prefetch of the next tile
     long long *trace;           // optional clock64() timeline of CTAs 0 and 1 (KOALA_TC_TRACE=1), else nullptr
 };
 
@@ -143,6 +145,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
                  "r"(c1)
                  : "memory");
+}
+// pull a contiguous global range into L2 (no smem, no completion): used to turn the next tile's first-touch HBM misses into L2 hits
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -243,7 +249,8 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     uint64_t *full_bar = bars, *empty_bar = bars + kStages;
     uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
     uint64_t *hp_full = bars + 2 * kStages + 4;                   // [2]: one per fp32 tile buffer
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 6);
+    uint64_t *staged = bars + 2 * kStages + 6;                    // [2]: h(t) of a pass is staged in shared memory
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 8);
     float *s_bias = reinterpret_cast<float *>(tail + 256);        // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -280,6 +287,8 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
         mbar_init(&hp_full[0], 1);
         mbar_init(&hp_full[1], 1);
+        mbar_init(&staged[0], kTcEpiThreads);
+        mbar_init(&staged[1], kTcEpiThreads);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc_pair(tmem_slot, 2 * kTcAccCols);
@@ -314,6 +323,21 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++pit) {
                 const int m = (tile / ctiles_n) * kPM + qm, n = (tile % ctiles_n) * kPN + qn;
                 if (warp == 0 && lane == 0) KTRACE(pit * 48 + 0);
+                if (kGru && is_a) {
+                    // my 64 rows of an activation operand are one contiguous 64 KB range: request the next tile's (and, at the
+                    // very start, this tile's) into L2 now, a whole mainloop before its loads are issued.  warp 0: x, warp 1: h
+                    const __nv_bfloat16 *src = warp == 0 ? args.a0 : args.a1;
+                    const uint32_t bytes = (uint32_t) (Cfg::kARowsPiece * args.H * 2);
+                    const int next = tile + num_clusters;
+                    if (elect_one()) {
+                        if (pit == 0) prefetch_l2(src + (size_t) (m * kTcPairM + (int) rank * kTcBlockM + qn * Cfg::kARowsPiece) * args.H, bytes);
+                        if (next < num_tiles) {
+                            const int m1 = (next / ctiles_n) * kPM + qm;
+                            prefetch_l2(src + (size_t) (m1 * kTcPairM + (int) rank * kTcBlockM + qn * Cfg::kARowsPiece) * args.H, bytes);
+                        }
+                    }
+                    __syncwarp();
+                }
                 for (int kb = par; kb < num_kb; kb += 2, g += 2) {
                     const int stage = (int) (g % kStages), phase = (int) ((g / kStages) & 1);
                     mbar_wait(&empty_bar[stage], phase ^ 1);     // slot free in every CTA of the cluster
@@ -378,6 +402,44 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 if (lane == 0) KTRACE(it * 48 + 3);
             }
         }
+    } else if (warp == kTcStateWarp) {
+        // ===================================================== GRU state traffic: one thread requests the fp32 h(t-1) box of every
+        // pass (two passes of 32 units per tile, pass c uses staging buffers c) and stores the fp32 / bf16 h(t) boxes the
+        // epilogue warps leave there.  Buffer c is refilled for the next tile as soon as its stores have been read out, a
+        // whole pass plus a mainloop before it is needed, and no epilogue thread ever waits on a store.
+        if (kGru && elect_one()) {
+            const int row0 = (int) rank * kTcBlockM;
+            if (cluster_id < num_tiles) {
+                const int m0 = (cluster_id / ctiles_n) * kPM + qm, n0 = (cluster_id % ctiles_n) * kPN + qn;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    mbar_expect_tx(&hp_full[c], Cfg::kEpiF32Bytes);
+                    tma_load_2d_local(&map_hp, &hp_full[c], s_hp + c * Cfg::kEpiF32Bytes, n0 * kGruUnits + 32 * c, m0 * kTcPairM + row0);
+                }
+            }
+            int it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+                const int m = (tile / ctiles_n) * kPM + qm, n = (tile % ctiles_n) * kPN + qn;
+                const int next = tile + num_clusters;
+                const int m1 = (next / ctiles_n) * kPM + qm, n1 = (next % ctiles_n) * kPN + qn;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint8_t *f32_box = s_hp + c * Cfg::kEpiF32Bytes, *b16_box = s_hb + c * (Cfg::kEpiBf16Bytes / 2);
+                    mbar_wait(&staged[c], it & 1);
+                    tma_store_2d(&map_hn, f32_box, n * kGruUnits + c * 32, m * kTcPairM + row0);
+                    tma_store_2d(&map_hb, b16_box, n * kGruUnits + c * 32, m * kTcPairM + row0);
+                    bulk_commit();
+                    KTRACE(it * 48 + 9 + c * 2);
+                    if (next < num_tiles) {
+                        bulk_wait_read();                        // the stores have read buffers c
+                        mbar_expect_tx(&hp_full[c], Cfg::kEpiF32Bytes);
+                        tma_load_2d_local(&map_hp, &hp_full[c], f32_box, n1 * kGruUnits + 32 * c, m1 * kTcPairM + row0);
+                    }
+                }
+            }
+            bulk_wait_all();                                     // shared memory must outlive the last stores
+        }
+        __syncwarp();
     } else if (warp >= 5) {
         // ===================================================== epilogue: warps 5..20.  TMEM lane quarter = warp % 4 (a warp can
         // only touch its own 32 lanes); the 4 warps of a quarter split the tile's columns (GRU: 16 of the 64 units each,
@@ -399,17 +461,8 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         mbar_arrive_cluster(empty_leader[0]);
         mbar_arrive_cluster(empty_leader[1]);
 
-        // GRU: the h(t-1) tile of my first tile starts travelling now (one thread drives the epilogue's TMA traffic)
         const int row_in_cta = quarter * 32 + lane;
         const int sw = row_in_cta & 7;
-        if (kGru && te == 0 && cluster_id < num_tiles) {
-            const int m0 = (cluster_id / ctiles_n) * kPM + qm, n0 = (cluster_id % ctiles_n) * kPN + qn;
-#pragma unroll
-            for (int p0 = 0; p0 < 2; ++p0) {
-                mbar_expect_tx(&hp_full[p0], Cfg::kEpiF32Bytes);
-                tma_load_2d_local(&map_hp, &hp_full[p0], s_hp + p0 * Cfg::kEpiF32Bytes, n0 * kGruUnits + 32 * p0, m0 * kTcPairM + (int) rank * kTcBlockM);
-            }
-        }
         constexpr float kL2e = 1.4426950408889634f;
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -436,12 +489,10 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             if (te == 0) KTRACE(it * 48 + 5);
             const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (kGru) {
-                // two passes of 32 units (pass c: units c * 32 .. c * 32 + 31 of the tile, 8 of them mine); pass buffers
-                // alternate, so h(t-1) of the next pass lands while this pass is computed and stored
-                const int r0 = m * kTcPairM + (int) rank * kTcBlockM, u0 = n * kGruUnits;
+                // two passes of 32 units (pass c: units c * 32 .. c * 32 + 31 of the tile, 8 of them mine), each with its own
+                // staging buffers, filled and drained by the state warp
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const int g = 2 * it + c;                    // running pass index: buffer c, phase it & 1
                     uint8_t *f32_box = s_hp + c * Cfg::kEpiF32Bytes, *b16_box = s_hb + c * (Cfg::kEpiBf16Bytes / 2);
                     uint8_t *f32_row = f32_box + row_in_cta * 128, *b16_row = b16_box + row_in_cta * 64;
                     const int cu = c * 32 + part * 8;            // first of my 8 units inside the tile
@@ -484,26 +535,8 @@ tc_masknet_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                             make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
                     *reinterpret_cast<uint4 *>(b16_row + part * 16) = pack_bf16x8(hn);
                     fence_proxy_async();                         // my smem writes -> visible to the TMA engine
-                    asm volatile("bar.sync 2, %0;" ::"n"(kTcEpiThreads) : "memory");
-                    if (te == 0) {
-                        tma_store_2d(&map_hn, f32_box, u0 + c * 32, r0);
-                        tma_store_2d(&map_hb, b16_box, u0 + c * 32, r0);
-                        bulk_commit();
-                        // the other pass buffer was stored one pass ago: once that store has read it, the h(t-1) of pass g + 1
-                        // ... g + 1 uses buffer c ^ 1, whose last store is the group before this one
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        const int gn = g + 1, itn = gn >> 1, cn = gn & 1;
-                        const int tile_n = cluster_id + itn * num_clusters;
-                        if (gn >= 2 && tile_n < num_tiles) {     // passes 0 and 1 were requested before the loop
-                            const int m1 = (tile_n / ctiles_n) * kPM + qm, n1 = (tile_n % ctiles_n) * kPN + qn;
-                            mbar_expect_tx(&hp_full[cn], Cfg::kEpiF32Bytes);
-                            tma_load_2d_local(&map_hp, &hp_full[cn], s_hp + cn * Cfg::kEpiF32Bytes, n1 * kGruUnits + 32 * cn,
-                                              m1 * kTcPairM + (int) rank * kTcBlockM);
-                        }
-                        KTRACE(it * 48 + 9 + c * 2);
-                    }
+                    mbar_arrive(&staged[c]);                     // state warp stores the pass once all 512 threads are here
                 }
-                if (te == 0 && tile + num_clusters >= num_tiles) bulk_wait_all();   // smem must outlive the last stores
             } else {
                 // my 32 of the tile's 128 outputs: bias + activation, staged in 128B-swizzled smem boxes, stored by TMA
                 if (te == 0) bulk_wait_read();                   // previous tile's stores have read the staging buffer
@@ -740,6 +773,7 @@ static int tc_masknet_step(TcPlan *p, int cur, cudaStream_t st, KernelProfiler *
         a.num_m_tiles = mt; a.num_n_tiles = H / kGruUnits; a.kb_per_part = H / kTcBlockK; a.H = H;
         a.bias0 = m.bih[l]; a.bias1 = m.bhh[l];
         a.h_prev = m.h[cur] + l * LBH; a.h_next = m.h[nxt] + l * LBH; a.out_bf16 = m.hb[nxt] + l * LBH;
+        a.a0 = l == 0 ? m.e : m.hb[nxt] + (l - 1) * LBH; a.a1 = m.hb[cur] + l * LBH;
         a.trace = (l == 0 && p->trace_kernel == 1) ? p->trace : nullptr;
         const CUtensorMap &ax = l == 0 ? p->a_e : p->a_hb[nxt][l - 1];
         if (prof) prof->begin(kKernGru, st);

@@ -12,7 +12,8 @@
 
 namespace koala {
 
-constexpr int kStftWarps = 8;
+constexpr int kStftWarps = 4;         // warps (= streams in flight) per CTA
+constexpr int kStftCtasPerSm = 7;     // 28 resident warps per SM: at most 72 registers per thread
 
 template <typename FeatT> __device__ __forceinline__ void store_feat8(FeatT *dst, const float (&f)[8]);
 template <> __device__ __forceinline__ void store_feat8<float>(float *dst, const float (&f)[8]) {
@@ -28,19 +29,21 @@ template <> __device__ __forceinline__ void store_feat8<__nv_bfloat16>(__nv_bflo
     *reinterpret_cast<uint4 *>(dst) = u;
 }
 
-// Persistent-style launch: grid = min(ceil(n / 8), 2 CTAs per SM), block = 256; each warp walks streams
-// s = blockIdx * 8 + warp, += gridDim * 8.
+// Launch: block = 128, grid = ceil(n / (4 * streams per warp)) with streams per warp chosen by the engine so that the whole
+// grid is resident at 7 CTAs per SM (8192 streams: 2 per warp, 1024 CTAs); warp w of CTA b walks streams
+// s = b * 4 + w, += gridDim * 4.
 // spec: [n][512] fp32 packed (Re, Im of bins 0..255; the Im slot of bin 0 carries Re X[256]).
 template <typename FeatT>
-__global__ void __launch_bounds__(kStftWarps * 32)
+__global__ void __launch_bounds__(kStftWarps * 32, kStftCtasPerSm)
 frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__restrict__ spec,
                 FeatT *__restrict__ feat, const float2 *__restrict__ lane_tab) {
     __shared__ __align__(16) int16_t s_frame[kStftWarps][kNfft];
+    __shared__ __align__(16) float2 s_tab[kLaneTabSmemRows * 32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
     FftLane c;
-    load_fft_lane(c, lane_tab, lane);      // constants: may be read before the previous kernel has finished
+    load_fft_lane(c, lane_tab, s_tab, lane);   // constants: may be read before the previous kernel has finished
     pdl_wait();
     const uint32_t *fw = reinterpret_cast<const uint32_t *>(s_frame[warp]);
     const int a = rev5(lane);
@@ -67,7 +70,8 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint32_t u = fw[lane + 32 * j];
-            z[j] = cpx{c.win[j].x * (float) (int16_t) (u & 0xffffu), c.win[j].y * (float) (int16_t) (u >> 16)};
+            const float2 w = c.win(j);
+            z[j] = cpx{w.x * (float) (int16_t) (u & 0xffffu), w.y * (float) (int16_t) (u >> 16)};
         }
         warp_fft256_dif(z, c, lane);
 
@@ -80,7 +84,8 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
             const cpx zp = shfl_c(z[partner_reg(j)], j == 0 ? src_a : src_b);
             const cpx E = {0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y)};
             const cpx O = {0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x)};
-            cpx x = cadd(E, cmul(O, cpx{c.tp[b].x, c.tp[b].y}));
+            const float2 w = c.tp(b);
+            cpx x = cadd(E, cmul(O, cpx{w.x, w.y}));
             if (j == 0 && lane == 0) x = cpx{zk.x + zk.y, zk.x - zk.y};   // (X[0], X[256]), both real
             X[b] = x;
         }
@@ -99,13 +104,14 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
 }
 
 // Same launch shape as frontend_kernel.  mask: [n][256] fp32.  ola: [n][256] fp32 state.
-__global__ void __launch_bounds__(kStftWarps * 32)
+__global__ void __launch_bounds__(kStftWarps * 32, kStftCtasPerSm)
 backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const float *__restrict__ mask,
                float *__restrict__ ola, const float2 *__restrict__ lane_tab) {
+    __shared__ __align__(16) float2 s_tab[kLaneTabSmemRows * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
     FftLane c;
-    load_fft_lane(c, lane_tab, lane);
+    load_fft_lane(c, lane_tab, s_tab, lane);
     pdl_wait();
     const int a = rev5(lane);
     const int src_a = rev5((32 - a) & 31), src_b = 31 - lane;
@@ -146,7 +152,8 @@ backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const f
             const cpx yp = shfl_c(Y[bp], j == 0 ? src_a : src_b);
             const cpx E = {0.5f * (yk.x + yp.x), 0.5f * (yk.y - yp.y)};
             const cpx D = {0.5f * (yk.x - yp.x), 0.5f * (yk.y + yp.y)};
-            const cpx O = cmulc(D, cpx{c.tp[b].x, c.tp[b].y});
+            const float2 w = c.tp(b);
+            const cpx O = cmulc(D, cpx{w.x, w.y});
             cpx zz = {E.x - O.y, E.y + O.x};
             if (j == 0 && lane == 0) zz = cpx{0.5f * (yk.x + yk.y), 0.5f * (yk.x - yk.y)};
             z[j] = zz;
@@ -158,15 +165,18 @@ backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const f
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int p = lane + 32 * j;
-            const float v0 = o[j].x + c.win[j].x * (z[j].x * inv), v1 = o[j].y + c.win[j].y * (z[j].y * inv);
+            const float2 w = c.win(j);
+            const float v0 = o[j].x + w.x * (z[j].x * inv), v1 = o[j].y + w.y * (z[j].y * inv);
             short i0, i1;   // round-to-nearest-even + saturate, the oracle's rintf + clamp
             asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i0) : "f"(v0));
             asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i1) : "f"(v1));
             out32[p] = (uint32_t) (uint16_t) i0 | ((uint32_t) (uint16_t) i1 << 16);
         }
 #pragma unroll
-        for (int j = 4; j < 8; ++j)
-            ola2[lane + 32 * (j - 4)] = make_float2(c.win[j].x * (z[j].x * inv), c.win[j].y * (z[j].y * inv));
+        for (int j = 4; j < 8; ++j) {
+            const float2 w = c.win(j);
+            ola2[lane + 32 * (j - 4)] = make_float2(w.x * (z[j].x * inv), w.y * (z[j].y * inv));
+        }
     }
 }
 
