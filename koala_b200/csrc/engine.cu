@@ -192,25 +192,34 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             KCHECK(upload(p->allocs, &p->bih[l], model.bih[l]));
             KCHECK(upload(p->allocs, &p->bhh[l], model.bhh[l]));
         }
-        // lane-major constants of the warp FFT (FftLane in koala_common.cuh): float2 [27][32], all computed in double
+        // lane-major constants of the warp FFT (FftLane / warp_fft256 in koala_common.cuh): float2 [25][32], computed in double.
+        // Rows 0-10: forward set, rows 11-21: inverse set (conjugate twiddles, bit-reversed lane index), row 22: split base,
+        // rows 23-24: window base angles.
         std::vector<float2> tab((size_t) kLaneTabRows * 32);
-        auto tw = [](int k) {
-            const double a = -2.0 * M_PI * (double) k / kNfft;
-            return make_float2((float) cos(a), (float) sin(a));
-        };
         auto rev5h = [](int v) { int r = 0; for (int b = 0; b < 5; b++) r |= ((v >> b) & 1) << (4 - b); return r; };
-        for (int lane = 0; lane < 32; lane++) {
-            for (int q = 0; q < 4; q++) tab[(0 + q) * 32 + lane] = tw((lane + 32 * q) * 2);
-            for (int q = 0; q < 2; q++) tab[(4 + q) * 32 + lane] = tw((lane + 32 * q) * 4);
-            tab[6 * 32 + lane] = tw(lane * 8);
-            for (int s = 0; s < 4; s++) {
-                const int h = 16 >> s;
-                tab[(7 + s) * 32 + lane] = tw((lane & (h - 1)) * (256 / h));
+        for (int dir = 0; dir < 2; dir++) {
+            auto w256 = [dir](int e, double sign) {       // W256^e (forward) or its conjugate (inverse), times sign
+                const double a = -2.0 * M_PI * (double) (e & 255) / 256.0;
+                return make_float2((float) (sign * cos(a)), (float) (sign * (dir == 0 ? sin(a) : -sin(a))));
+            };
+            float2 *t = tab.data() + (size_t) (dir == 0 ? 0 : kLaneTabInv) * 32;
+            for (int lane = 0; lane < 32; lane++) {
+                const int base = dir == 0 ? lane : rev5h(lane);    // low five index bits held by this lane
+                for (int q = 0; q < 4; q++) t[(0 + q) * 32 + lane] = w256(base + 32 * q, 1.0);
+                for (int q = 0; q < 2; q++) t[(4 + q) * 32 + lane] = w256(2 * (base + 32 * q), 1.0);
+                t[6 * 32 + lane] = w256(4 * base, 1.0);
+                for (int i = 0; i < 4; i++) {                      // swapped stages on index bit 4 - i
+                    const int bit = 4 - i, h = dir == 0 ? (16 >> i) : (1 << i);
+                    t[(7 + i) * 32 + lane] = w256((base & ((1 << bit) - 1)) << (7 - bit), (lane & h) ? -1.0 : 1.0);
+                }
             }
-            for (int b = 0; b < 8; b++) tab[(11 + b) * 32 + lane] = tw(8 * rev5h(lane) + b);
-            for (int j = 0; j < 8; j++) {
-                const int p2 = 2 * (lane + 32 * j);
-                tab[(19 + j) * 32 + lane] = make_float2((float) sin(M_PI * (double) p2 / kNfft), (float) sin(M_PI * (double) (p2 + 1) / kNfft));
+        }
+        for (int lane = 0; lane < 32; lane++) {
+            const double a = -2.0 * M_PI * (double) rev5h(lane) / kNfft;
+            tab[(size_t) kLaneTabSplit * 32 + lane] = make_float2((float) cos(a), (float) sin(a));
+            for (int o = 0; o < 2; o++) {
+                const double th = M_PI * (double) (2 * lane + o) / kNfft;
+                tab[(size_t) (kLaneTabWin + o) * 32 + lane] = make_float2((float) sin(th), (float) cos(th));
             }
         }
         KCHECK(upload(p->allocs, &p->tables, tab));

@@ -92,29 +92,33 @@ __device__ __forceinline__ cpx shfl_c(cpx v, int src) {
 }
 __device__ __forceinline__ int rev5(int v) { return (int) (__brev((unsigned) v) >> 27); }
 
-// Per-lane constants of the warp FFT.  The host lays them out lane-major (float2 [kLaneTabRows][32]): lane l's copy of
-// constant i is tab[i * 32 + l], so a row is one coalesced 256-byte request from global memory and a conflict-free access
-// from shared memory (the first version indexed twiddles by bin, with up to 16-way bank conflicts: profiles/r01_step_summary.md).
-// The twiddles of the butterfly stages (rows 0-10) are used by every stage and live in registers for all streams a warp
-// walks; the real-FFT split factors and the window (rows 11-26) are used once per frame and stay in shared memory, which
-// keeps the kernels under 72 registers = 28 resident warps per SM (these kernels are latency-bound: occupancy is speed).
-constexpr int kLaneTabRows = 27;
-constexpr int kLaneTabRegRows = 11;                               // t4, t2, t1, tx
-constexpr int kLaneTabSmemRows = kLaneTabRows - kLaneTabRegRows;  // tp[8], win[8]
+// One warp = one 256-point complex FFT, 8 points per lane, radix-2 decimation in frequency.
+//
+// A butterfly stage needs both elements of a pair in the same lane.  The three high index bits start out as the register
+// index; each of the five low bits lives in the lane id and is first SWAPPED with an already-processed register bit (lane
+// l and lane l ^ h exchange half of their registers: 8 shuffles per stage, half of what a butterfly across lanes costs)
+// and then processed in registers.  These kernels are bound by the LSU data pipe that executes shuffles and shared-memory
+// accesses at one wavefront per two cycles (profiles/r01_step_summary.md), so shuffles are what is being minimised: 40 per
+// transform, no shared memory.
+//
+// The same routine runs both directions; only the bit bookkeeping and the twiddle tables differ:
+//   forward: in  z[j] = x[lane + 32 j]                       out z[j] = Z[k], k = rev5(lane) + 32 m, m = (j1 j2 j0)
+//   inverse: in  that frequency layout                        out z[j] = 256 x[lane + 32 j]
+// (j2 j1 j0 = bits of the register index j; "m = (j1 j2 j0)" means m bit 2 = j bit 1, m bit 1 = j bit 2, m bit 0 = j bit 0).
+// Twiddles are per-lane constants, laid out lane-major by the host (float2 [kLaneTabRows][32], engine.cu): a row is one
+// coalesced 256-byte load, and they stay in registers for all streams a warp walks.
+constexpr int kLaneTabRows = 25;
+constexpr int kLaneTabInv = 11;      // first row of the inverse set
+constexpr int kLaneTabSplit = 22;    // W512^c, c = rev5(lane)
+constexpr int kLaneTabWin = 23;      // (sin, cos) of pi (2 lane) / 512 and of pi (2 lane + 1) / 512
 struct FftLane {
-    float2 t4[4];    // span 128: W512^{2 (lane + 32 q)},  q = j & 3
-    float2 t2[2];    // span  64: W512^{4 (lane + 32 q)},  q = j & 1
-    float2 t1;       // span  32: W512^{8 lane}
-    float2 tx[4];    // spans 16, 8, 4, 2 (lane exchange): W512^{(lane & (h-1)) * 256 / h}
-    const float2 *sm;  // shared-memory rows of this lane: tp(b) = real-FFT split W512^{8 rev5(lane) + b}; win(j) = sqrt-Hann
-                       // window pair (w[2p], w[2p+1]), p = lane + 32 j
-    __device__ __forceinline__ float2 tp(int b) const { return sm[32 * b]; }
-    __device__ __forceinline__ float2 win(int j) const { return sm[32 * (8 + j)]; }
+    float2 t4[4];    // first stage:  W256^(b + 32 q), q = the two register bits still to come;  b = low five index bits of the lane
+    float2 t2[2];    // second stage: W128^(b + 32 q), q = the last register bit
+    float2 t1;       // third stage:  W64^b
+    float2 tx[4];    // swapped stages t = 4..1: W_{2^(t+1)}^(b mod 2^t), negated in the lanes whose swapped bit is set
 };
-// s_tab: float2 [kLaneTabSmemRows * 32] of shared memory, filled by the whole CTA (ends with __syncthreads)
-__device__ __forceinline__ void load_fft_lane(FftLane &c, const float2 *__restrict__ tab, float2 *s_tab, int lane) {
-    for (int i = threadIdx.x; i < kLaneTabSmemRows * 32; i += blockDim.x) s_tab[i] = __ldg(tab + kLaneTabRegRows * 32 + i);
-    const float2 *t = tab + lane;
+__device__ __forceinline__ void load_fft_lane(FftLane &c, const float2 *__restrict__ tab, int lane, bool inverse) {
+    const float2 *t = tab + (inverse ? kLaneTabInv * 32 : 0) + lane;
 #pragma unroll
     for (int i = 0; i < 4; ++i) c.t4[i] = __ldg(t + 32 * i);
 #pragma unroll
@@ -122,76 +126,76 @@ __device__ __forceinline__ void load_fft_lane(FftLane &c, const float2 *__restri
     c.t1 = __ldg(t + 32 * 6);
 #pragma unroll
     for (int i = 0; i < 4; ++i) c.tx[i] = __ldg(t + 32 * (7 + i));
-    c.sm = s_tab + lane;
-    __syncthreads();
 }
 
-// One warp = one 256-point complex FFT.  Lane l, register j hold element p = l + 32 j.
-// Forward: radix-2 DIF, natural order in -> bit-reversed out: after the call z[j] = Z[8 * rev5(lane) + rev3(j)].
-__device__ __forceinline__ void warp_fft256_dif(cpx (&z)[8], const FftLane &c, int lane) {
+template <bool INV>
+__device__ __forceinline__ void warp_fft256(cpx (&z)[8], const FftLane &c, int lane) {
+    // register bits of the three in-register stages, in processing order (index bits 7, 6, 5)
+    constexpr int RB0 = INV ? 2 : 4, RB1 = INV ? 4 : 2, RB2 = 1;
 #pragma unroll
-    for (int dj = 4; dj >= 1; dj >>= 1) {   // spans 128, 64, 32: partner is another register of the same lane
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j & dj) continue;
-            const float2 w2 = dj == 4 ? c.t4[j & 3] : dj == 2 ? c.t2[j & 1] : c.t1;
-            const cpx a = z[j], b = z[j + dj];
-            z[j] = cadd(a, b);
-            z[j + dj] = cmul(csub(a, b), cpx{w2.x, w2.y});
-        }
+    for (int j = 0; j < 8; ++j) {
+        if (j & RB0) continue;
+        const float2 w = c.t4[((j & RB1) ? 2 : 0) | ((j & RB2) ? 1 : 0)];
+        const cpx a = z[j], b = z[j | RB0];
+        z[j] = cadd(a, b);
+        z[j | RB0] = cmul(csub(a, b), cpx{w.x, w.y});
     }
-    // spans 16..1: partner is lane ^ h.  Branch-free butterfly: both lanes compute (o + sgn * v) * w' with sgn = -1 and
-    // w' = twiddle in the upper lane, sgn = +1 and w' = 1 in the lower lane (6 arithmetic instructions + 2 shuffles per point)
 #pragma unroll
-    for (int s = 0; s < 5; ++s) {
-        const int h = 16 >> s;
+    for (int j = 0; j < 8; ++j) {
+        if (j & RB1) continue;
+        const float2 w = c.t2[(j & RB2) ? 1 : 0];
+        const cpx a = z[j], b = z[j | RB1];
+        z[j] = cadd(a, b);
+        z[j | RB1] = cmul(csub(a, b), cpx{w.x, w.y});
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j & RB2) continue;
+        const cpx a = z[j], b = z[j | RB2];
+        z[j] = cadd(a, b);
+        z[j | RB2] = cmul(csub(a, b), cpx{c.t1.x, c.t1.y});
+    }
+    // index bits 4..0: lane bit h <-> register bit d, then the stage on register bit d.  The lane with bit h clear keeps its
+    // d = 0 registers and receives the partner's, the other lane keeps d = 1: `kept` and `recv` are then the two elements of a
+    // pair, in the order (a, b) in the lower lane and (b, a) in the upper one; a + b is symmetric and the sign of a - b is
+    // folded into the upper lanes' twiddle.
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int h = INV ? (1 << i) : (16 >> i);
+        const int d = INV ? (i == 0 ? 2 : i == 1 ? 4 : i == 2 ? 1 : i == 3 ? 2 : 4) : (i == 0 ? 4 : i == 1 ? 2 : i == 2 ? 1 : i == 3 ? 4 : 2);
         const bool up = (lane & h) != 0;
         const float sgn = up ? -1.0f : 1.0f;
-        const cpx w = (s < 4 && up) ? cpx{c.tx[s < 4 ? s : 0].x, c.tx[s < 4 ? s : 0].y} : cpx{1.0f, 0.0f};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const cpx v = z[j], o = shfl_xor_c(v, h);
-            const cpx t = {fmaf(sgn, v.x, o.x), fmaf(sgn, v.y, o.y)};
-            z[j] = s < 4 ? cmul(t, w) : t;   // span 1: twiddle is 1 for everyone
+            if (j & d) continue;
+            const cpx kept = up ? z[j | d] : z[j], send = up ? z[j] : z[j | d];
+            const cpx recv = shfl_xor_c(send, h);
+            z[j] = cadd(kept, recv);
+            const cpx df = csub(kept, recv);
+            z[j | d] = i < 4 ? cmul(df, cpx{c.tx[i < 4 ? i : 0].x, c.tx[i < 4 ? i : 0].y}) : cpx{sgn * df.x, sgn * df.y};
         }
     }
 }
 
-// Inverse: radix-2 DIT with conjugate twiddles, bit-reversed in (layout produced by warp_fft256_dif) -> natural out.
-// No 1/256 scaling is applied.
-__device__ __forceinline__ void warp_ifft256_dit(cpx (&z)[8], const FftLane &c, int lane) {
-    // spans 1, 2, 4, 8, 16: upper lane first scales by conj(twiddle) (lower lane by 1), then out = o + sgn * t
-#pragma unroll
-    for (int s = 4; s >= 0; --s) {
-        const int h = 16 >> s;
-        const bool up = (lane & h) != 0;
-        const float sgn = up ? -1.0f : 1.0f;
-        const cpx w = (s < 4 && up) ? cpx{c.tx[s < 4 ? s : 0].x, c.tx[s < 4 ? s : 0].y} : cpx{1.0f, 0.0f};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const cpx t = s < 4 ? cmulc(z[j], w) : z[j];
-            const cpx o = shfl_xor_c(t, h);
-            z[j] = cpx{fmaf(sgn, t.x, o.x), fmaf(sgn, t.y, o.y)};
-        }
-    }
-#pragma unroll
-    for (int dj = 1; dj <= 4; dj <<= 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j & dj) continue;
-            const float2 w2 = dj == 4 ? c.t4[j & 3] : dj == 2 ? c.t2[j & 1] : c.t1;
-            const cpx a = z[j], b = cmulc(z[j + dj], cpx{w2.x, w2.y});
-            z[j] = cadd(a, b);
-            z[j + dj] = csub(a, b);
-        }
-    }
-}
+// Frequency layout shared by the two kernels (output of the forward transform): lane holds the bins k = c + 32 m,
+// c = rev5(lane), m = 0..7, in register kFftRegOfM[m].  The partner bin 256 - k of the real-FFT split is bin (32 - c) + 32 (7 - m):
+// always the same lane rev5((32 - c) & 31), register kFftRegOfM[7 - m] -- except c = 0, whose partners are its own registers.
+__device__ __forceinline__ constexpr int fft_reg_of_m(int m) { return m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 4 : m == 3 ? 5 : m == 4 ? 2 : m == 5 ? 3 : m == 6 ? 6 : 7; }
 
-// register index holding the partner bin 256 - k of register j (k = 8 a + rev3(j)); see DESIGN.md "FFT layout"
-__device__ __forceinline__ constexpr int partner_reg(int j) {
-    return j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 3 : j == 3 ? 2 : j == 4 ? 7 : j == 5 ? 6 : j == 6 ? 5 : 4;
+// sqrt-Hann window pair (w[2p], w[2p + 1]) of complex point p = lane + 32 j from the lane's base angles: sin(t + j pi / 8)
+__device__ __forceinline__ float2 window_pair(const float2 &we, const float2 &wo, int j) {
+    constexpr float cs[8] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                             0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+    constexpr float sn[8] = {0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                             1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+    return make_float2(fmaf(we.x, cs[j], we.y * sn[j]), fmaf(wo.x, cs[j], wo.y * sn[j]));
 }
-__device__ __forceinline__ constexpr int rev3c(int j) { return ((j & 1) << 2) | (j & 2) | ((j >> 2) & 1); }
+// W512^(c + 32 m) = W512^c * exp(-i pi m / 8), m = 0..3
+__device__ __forceinline__ cpx split_twiddle(const float2 &base, int m) {
+    constexpr float cs[4] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+    constexpr float sn[4] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+    return m == 0 ? cpx{base.x, base.y} : cmul(cpx{base.x, base.y}, cpx{cs[m], sn[m]});
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // mbarrier helpers shared by the TMA / tcgen05 pipelines
