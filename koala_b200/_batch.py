@@ -116,7 +116,7 @@ class BatchKoala(object):
         check(self._library, self._library.pv_koala_batch_kernel_launches(self._handle, byref(n)), 'launch count failed')
         return n.value
 
-    KERNEL_CLASSES = ("frontend", "enc", "gru", "dec", "backend")
+    KERNEL_CLASSES = ("frontend", "enc", "gru", "dec", "backend", "masknet")
 
     def profile(self, enable: bool) -> None:
         check(self._library, self._library.pv_koala_batch_profile(self._handle, 1 if enable else 0), 'profile failed')

@@ -26,7 +26,8 @@ constexpr float kFeatBias = 0.25f;
 enum Precision : int { kFp32 = 0, kBf16 = 1 };
 
 // kernel classes of one step, in launch order (per-class timing for bench.py's roofline object)
-enum KernelClass : int { kKernFrontend = 0, kKernEnc = 1, kKernGru = 2, kKernDec = 3, kKernBackend = 4, kKernClasses = 5 };
+// (kKernMasknet: the fused encoder -> GRU -> decoder kernel of the bf16 path; Enc / Gru / Dec: the fp32 path's separate kernels)
+enum KernelClass : int { kKernFrontend = 0, kKernEnc = 1, kKernGru = 2, kKernDec = 3, kKernBackend = 4, kKernMasknet = 5, kKernClasses = 6 };
 
 // Optional per-launch CUDA-event timing on the launching stream (off by default: events perturb back-to-back launches).
 struct KernelProfiler {
