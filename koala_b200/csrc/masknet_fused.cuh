@@ -32,7 +32,7 @@
 namespace koala {
 
 #ifndef KOALA_FU_STAGES
-#define KOALA_FU_STAGES 6
+#define KOALA_FU_STAGES 5
 #endif
 constexpr int kFuStages = KOALA_FU_STAGES;
 constexpr int kFuStageBytes = kTcABytes + (kGruRows / 2) * 128;   // 28 KB: A [128][64] + B up to [96][64] bf16 (linear tiles: 64 rows)
@@ -42,8 +42,17 @@ constexpr int kFuARows = kTcBlockM / kFuPN;                       // rows of A e
 constexpr int kFuLinN = 128;                                      // outputs per linear pair tile
 constexpr int kFuBoxF32 = kTcBlockM * 32 * 4;                     // staging box [128 rows][32 fp32], 128B-swizzled
 constexpr int kFuBoxB16 = kTcBlockM * 32 * 2;                     // staging box [128 rows][32 bf16], plain
-constexpr int kFuSmemBytes = kFuStages * kFuStageBytes + 2 * (kFuBoxF32 + kFuBoxB16) + kTcTailBytes;
+constexpr int kFuLinBytes = 2 * kFuBoxF32;                       // linear tiles: staging for [128][128] bf16 or [128][64] fp32 (two swizzled boxes)
+constexpr int kFuLinWarp = kTcStateWarp + 1;                      // stores the linear tiles' staged outputs
+constexpr int kFuThreads = kTcThreads + 32;
+constexpr int kFuSmemBytes = kFuStages * kFuStageBytes + 2 * (kFuBoxF32 + kFuBoxB16) + kFuLinBytes + kTcTailBytes;
 constexpr int kFuMaxSegs = kMaxLayers + 2;
+#ifdef KOALA_FU_THREAD_ARRIVE
+constexpr bool kFuWarpArrive = false;
+#else
+constexpr bool kFuWarpArrive = true;     // one mbarrier arrival per epilogue warp instead of one per thread
+#endif
+constexpr int kFuArrivals = kFuWarpArrive ? kTcEpiWarps : kTcEpiThreads;
 enum FuMap : int { kMapA0 = 0, kMapA1, kMapB0, kMapB1, kMapHp, kMapHn, kMapHb, kFuMapsPerSeg };
 
 struct FuSeg {
@@ -78,6 +87,7 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
 __device__ __forceinline__ void red_release_gpu(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void bulk_wait_read_but1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // position of one cluster in the global tile list
@@ -91,20 +101,22 @@ __device__ __forceinline__ FuTile fu_decode(const FuArgs &a, int g) {
     return FuTile{s, local / nc, (local % nc) * kFuPN};
 }
 
-__global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads, 1) tc_fused_kernel(const __grid_constant__ FuArgs args) {
+__global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads, 1) tc_fused_kernel(const __grid_constant__ FuArgs args) {
     constexpr int kStages = kFuStages, kStageBytes = kFuStageBytes;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
     uint8_t *s_f32 = smem + kStages * kStageBytes;       // 2 fp32 staging boxes
     uint8_t *s_b16 = s_f32 + 2 * kFuBoxF32;              // 2 bf16 staging boxes
-    uint8_t *tail = s_b16 + 2 * kFuBoxB16;
+    uint8_t *s_lin = s_b16 + 2 * kFuBoxB16;              // linear tiles' staging: two 16 KB swizzled boxes
+    uint8_t *tail = s_lin + kFuLinBytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
     uint64_t *full_bar = bars, *empty_bar = bars + kStages;
     uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
     uint64_t *box_ready = bars + 2 * kStages + 4;        // [2]: staging buffer is free (linear) / holds h(t-1) (GRU)
     uint64_t *staged = bars + 2 * kStages + 6;           // [2]: the epilogue has staged a pass in the buffer
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 8);
+    uint64_t *lin_free = bars + 2 * kStages + 8, *lin_staged = bars + 2 * kStages + 9;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 10);
     float *s_bias = reinterpret_cast<float *>(tail + 256);   // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,7 +126,12 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
     const int qn = (int) (crank >> 1);             // my pair's n tile inside the cluster tile
     const uint16_t pair_mask = (uint16_t) (3u << leader), all_mask = (uint16_t) ((1u << kFuCluster) - 1);
     long long *trace = (args.trace != nullptr && blockIdx.x < 2) ? args.trace + blockIdx.x * 1024 : nullptr;
+    (void) trace;
+#ifdef KOALA_FU_TRACE      // clock64 timeline of cluster 0 (tools/gpu_trace.py builds this variant); compiled out of the product
 #define KTRACE(slot) do { if (trace && (slot) < 1024) trace[(slot)] = clock64(); } while (0)
+#else
+#define KTRACE(slot) do { } while (0)
+#endif
     if (threadIdx.x == 0) KTRACE(1020);
     pdl_launch_dependents();
     const int cluster_id = blockIdx.x / kFuCluster, num_clusters = gridDim.x / kFuCluster;
@@ -129,10 +146,12 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&tmem_full[b], 1);         // one multicast tcgen05.commit
-                mbar_init(&tmem_empty[b], 2 * kTcEpiThreads);   // leader's copy: the epilogue threads of both CTAs
+                mbar_init(&tmem_empty[b], 2 * kFuArrivals);     // leader's copy: the epilogue warps (threads) of both CTAs
                 mbar_init(&box_ready[b], 1);
-                mbar_init(&staged[b], kTcEpiThreads);
+                mbar_init(&staged[b], kFuArrivals);
             }
+            mbar_init(lin_free, 1);
+            mbar_init(lin_staged, kFuArrivals);
             fence_mbar_init();
         }
     }
@@ -197,7 +216,12 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
                 const int kc = (second ? kb - sg.kb_per_part : kb) * kTcBlockK;
                 if (!elected) {
                 } else if (is_a) {
+#ifdef KOALA_FU_NO_MC      // diagnostic: every CTA fetches both 64-row pieces of its A block itself
+                    for (int j = 0; j < kFuPN; ++j)
+                        tma_load_2d_pair(maps + (second ? kMapA1 : kMapA0), full_leader, sa + j * kFuARows * 128, kc, t.m * kTcPairM + (int) rank * kTcBlockM + j * kFuARows);
+#else
                     tma_load_2d_pair_mc(maps + (second ? kMapA1 : kMapA0), full_leader, sa + qn * kFuARows * 128, kc, arow_of(t.m), mask_a);
+#endif
                 } else {
                     tma_load_2d_pair(maps + (second ? kMapB1 : kMapB0), full_leader, sb, kc, n * 2 * brows + (int) rank * brows);
                 }
@@ -236,6 +260,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
         // ===================================================== MMA issuer (one thread of the leader CTA drives both SMs)
         if (rank == 0) {
             int stage = 0, phase = 0, it = 0;
+            const uint64_t adesc0 = make_sw128_desc(smem_u32(smem)), bdesc0 = make_sw128_desc(smem_u32(smem) + kTcABytes);
             for (int g = cluster_id; g < total; g += num_clusters, ++it) {
                 const FuTile t = fu_decode(args, g);
                 const FuSeg &sg = args.seg[t.s];
@@ -251,13 +276,13 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (lane == 0) KTRACE(it * 48 + 32 + kb);
-                    const uint32_t sa = smem_u32(smem + stage * kStageBytes), sb = sa + kTcABytes;
-                    const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sb);
                     const bool hpart = gru && kb >= kbp;   // GRU h-part: columns [r | z | n_h], always accumulating
+                    const uint32_t dk = hpart ? d + kGruUnits : d, acc0 = hpart ? 1u : (uint32_t) (kb != 0);
                     if (elect_one()) {
+                        const uint64_t so = (uint64_t) ((stage * kStageBytes) >> 4);
 #pragma unroll
                         for (int k = 0; k < kTcBlockK / 16; ++k)    // +32 B per 16-element k-step
-                            umma_bf16_pair(hpart ? d + kGruUnits : d, adesc + 2 * k, bdesc + 2 * k, idesc, hpart ? 1u : (uint32_t) ((kb | k) != 0));
+                            umma_bf16_pair(dk, adesc0 + so + 2 * k, bdesc0 + so + 2 * k, idesc, k == 0 ? acc0 : 1u);
                         umma_commit_pair(&empty_bar[stage], all_mask);   // partners multicast into my slots, so everyone must know
                     }
                     __syncwarp();
@@ -269,41 +294,37 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
             }
         }
     } else if (warp == kTcStateWarp) {
-        // ===================================================== state warp: one thread moves every pass's staging boxes.  `cur`
-        // walks the passes in order (wait until staged, store, commit); `ahead` runs two passes in front and re-arms the
-        // buffer that `cur` just drained.  After a tile's last pass it waits for the stores to COMPLETE and bumps the
-        // segment's counter for the m tile, which releases the dependent tiles of the next segment.
+        // ===================================================== state warp: one thread moves the staging boxes of the GRU tiles
+        // (two passes of 32 units each).  `cur` walks the passes in order (wait until staged, store fp32 + bf16 h(t), commit);
+        // `ahead` runs two passes in front and requests the fp32 h(t-1) box of that pass into the buffer `cur` just drained,
+        // a whole mainloop before the epilogue needs it.  After a tile's second pass it waits for the stores to COMPLETE and
+        // bumps the segment's counter for the m tile, which releases the dependent tiles of the next segment.
         pdl_wait();
         if (elect_one()) {
             const int row0 = (int) rank * kTcBlockM;
             struct PassIter {
-                int g, c, npass;
+                int g, c;
                 FuTile t;
             };
-            auto start = [&](PassIter &p, int g) {
+            auto start = [&](PassIter &p, int g) {           // first pass of the cluster's next GRU tile at or after g
+                for (; g < total; g += num_clusters) {
+                    p.t = fu_decode(args, g);
+                    if (args.seg[p.t.s].mode == kTcGru) break;
+                }
                 p.g = g;
                 p.c = 0;
-                if (g < total) {
-                    p.t = fu_decode(args, g);
-                    p.npass = args.seg[p.t.s].mode == kTcGru ? 2 : 4;
-                }
             };
             auto advance = [&](PassIter &p) {
-                if (++p.c == p.npass) start(p, p.g + num_clusters);
+                if (++p.c == 2) start(p, p.g + num_clusters);
             };
-            auto arm = [&](const PassIter &p, int buf) {     // make staging buffer `buf` ready for pass p
-                const FuSeg &sg = args.seg[p.t.s];
-                if (sg.mode == kTcGru) {
-                    mbar_expect_tx(&box_ready[buf], kFuBoxF32);
-                    tma_load_2d_local(args.maps + p.t.s * kFuMapsPerSeg + kMapHp, &box_ready[buf], s_f32 + buf * kFuBoxF32,
-                                      (p.t.n0 + qn) * kGruUnits + 32 * p.c, p.t.m * kTcPairM + row0);
-                } else {
-                    mbar_arrive(&box_ready[buf]);
-                }
+            auto arm = [&](const PassIter &p, int buf) {     // request the fp32 h(t-1) box of pass p into staging buffer `buf`
+                mbar_expect_tx(&box_ready[buf], kFuBoxF32);
+                tma_load_2d_local(args.maps + p.t.s * kFuMapsPerSeg + kMapHp, &box_ready[buf], s_f32 + buf * kFuBoxF32,
+                                  (p.t.n0 + qn) * kGruUnits + 32 * p.c, p.t.m * kTcPairM + row0);
             };
             PassIter cur, ahead;
             start(cur, cluster_id);
-            start(ahead, cluster_id);
+            ahead = cur;
             for (int b = 0; b < 2 && ahead.g < total; ++b) {
                 arm(ahead, b);
                 advance(ahead);
@@ -314,11 +335,10 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
                 const int buf = (int) (pc & 1);
                 const FuSeg &sg = args.seg[cur.t.s];
                 const CUtensorMap *maps = args.maps + cur.t.s * kFuMapsPerSeg;
-                const int n = cur.t.n0 + qn, row = cur.t.m * kTcPairM + row0;
-                const int col = (sg.mode == kTcGru ? n * kGruUnits : n * kFuLinN) + 32 * cur.c;
+                const int row = cur.t.m * kTcPairM + row0, col = (cur.t.n0 + qn) * kGruUnits + 32 * cur.c;
                 mbar_wait(&staged[buf], (pc >> 1) & 1);
-                if (sg.mode != kTcEnc) tma_store_2d(maps + kMapHn, s_f32 + buf * kFuBoxF32, col, row);
-                if (sg.mode != kTcDec) tma_store_2d(maps + kMapHb, s_b16 + buf * kFuBoxB16, col, row);
+                tma_store_2d(maps + kMapHn, s_f32 + buf * kFuBoxF32, col, row);
+                tma_store_2d(maps + kMapHb, s_b16 + buf * kFuBoxB16, col, row);
                 bulk_commit();
                 KTRACE(it * 48 + 9 + (cur.c & 1) * 2);
                 if (ahead.g < total) {
@@ -326,7 +346,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
                     arm(ahead, buf);
                     advance(ahead);
                 }
-                if (cur.c + 1 == cur.npass) {
+                if (cur.c == 1) {
                     if (sg.done >= 0) {
                         bulk_wait_all();                     // this tile's rows are in global memory
                         fence_proxy_async_all();
@@ -340,7 +360,46 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
             bulk_wait_all();                                 // shared memory must outlive the last stores
         }
         __syncwarp();
-    } else if (warp >= 5) {
+    } else if (warp == kFuLinWarp) {
+        // ===================================================== linear-tile store warp: encoder / decoder outputs leave through
+        // their own 32 KB staging region in ROUNDS (encoder: the whole [128][128] bf16 tile of this CTA, decoder: two halves
+        // of [128][64] fp32), so they never compete with the GRU passes for staging buffers.  Per round: wait until the
+        // epilogue warps have staged it, TMA-store its two boxes, free the region once they have been read; after an encoder
+        // tile, wait for the stores to complete and release the dependent GRU tiles.
+        pdl_wait();
+        if (elect_one()) {
+            const int row0 = (int) rank * kTcBlockM;
+            unsigned lc = 0;
+            for (int g = cluster_id; g < total; g += num_clusters) {
+                const FuTile t = fu_decode(args, g);
+                const FuSeg &sg = args.seg[t.s];
+                if (sg.mode == kTcGru) continue;
+                const CUtensorMap *map = args.maps + t.s * kFuMapsPerSeg + kMapHn;
+                const int row = t.m * kTcPairM + row0, col = (t.n0 + qn) * kFuLinN;
+                const int rounds = sg.mode == kTcEnc ? 1 : 2;
+                for (int h = 0; h < rounds; ++h, ++lc) {
+                    mbar_wait(lin_staged, lc & 1);
+                    if (sg.mode == kTcEnc) {       // boxes of 64 bf16 columns
+                        tma_store_2d(map, s_lin, col, row);
+                        tma_store_2d(map, s_lin + kFuBoxF32, col + 64, row);
+                    } else {                       // boxes of 32 fp32 columns
+                        tma_store_2d(map, s_lin, col + 64 * h, row);
+                        tma_store_2d(map, s_lin + kFuBoxF32, col + 64 * h + 32, row);
+                    }
+                    bulk_commit();
+                    bulk_wait_read();
+                    mbar_arrive(lin_free);
+                }
+                if (sg.done >= 0) {
+                    bulk_wait_all();                         // this tile's rows are in global memory
+                    fence_proxy_async_all();
+                    red_release_gpu(args.counters + (size_t) sg.done * args.num_m_tiles + t.m, 1u);
+                }
+            }
+            bulk_wait_all();
+        }
+        __syncwarp();
+    } else if (warp >= 5 && warp < kTcStateWarp) {
         // ===================================================== epilogue: warps 5..20.  TMEM lane quarter = warp % 4 (a warp can
         // only touch its own 32 lanes); the 4 warps of a quarter take 8 of a pass's 32 columns each.  16 warps, not 8: the
         // gate math is a long dependent chain (5 MUFU ops per unit) and needs the extra warps per scheduler to hide it.
@@ -355,13 +414,16 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive_cluster(empty_leader[0]);
-        mbar_arrive_cluster(empty_leader[1]);
+        __syncwarp();
+        if (kFuWarpArrive ? lane == 0 : true) {
+            mbar_arrive_cluster(empty_leader[0]);
+            mbar_arrive_cluster(empty_leader[1]);
+        }
 
         const int row_in_cta = quarter * 32 + lane;
         const int sw = row_in_cta & 7;
         constexpr float kL2e = 1.4426950408889634f;
-        unsigned pc = 0;
+        unsigned pc = 0, lc = 0;       // GRU passes / linear rounds so far: staging buffer and barrier phase
         int it = 0;
         for (int g = cluster_id; g < total; g += num_clusters, ++it) {
             const FuTile t = fu_decode(args, g);
@@ -388,66 +450,92 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kTcThreads,
             tc_fence_after();
             if (te == 0) KTRACE(it * 48 + 5);
             const uint32_t t0 = lane_base + ab * kTcAccCols;
-            const int npass = mode == kTcGru ? 2 : 4;
-            for (int c = 0; c < npass; ++c, ++pc) {
+            if (mode != kTcGru) {
+                // linear tile: my warp owns 32 of the 128 outputs (columns part * 32 ..), one row per thread.  The accumulator
+                // buffer is handed back after four TMEM loads; the outputs are staged in the linear staging region (128B-
+                // swizzled boxes) and stored by the linear store warp: the encoder's tile in one round, the decoder's fp32
+                // tile in two rounds of 64 columns (warps with part / 2 == round write).
+                float acc[32];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tmem_ld8(t0 + part * 32 + 8 * j, *reinterpret_cast<float(*)[8]>(acc + 8 * j));
+                tmem_ld_wait();
+                tc_fence_before();
+                if (te == 0) KTRACE(it * 48 + 6);
+                __syncwarp();
+                if (kFuWarpArrive ? lane == 0 : true) mbar_arrive_cluster(empty_leader[ab]);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float v = acc[i] + sb[part * 32 + i];
+                    acc[i] = mode == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
+                }
+                const int rounds = mode == kTcEnc ? 1 : 2;
+                for (int h = 0; h < rounds; ++h, ++lc) {
+                    mbar_wait(lin_free, (lc & 1) ^ 1);       // the previous round's stores have read the region
+                    if (mode == kTcEnc) {                    // box part / 2 holds columns 64 (part / 2) ..; my 32 columns = 4 chunks of 8 bf16
+                        uint8_t *rowp = s_lin + (part >> 1) * kFuBoxF32 + row_in_cta * 128;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + j) ^ sw) << 4)) = pack_bf16x8(acc + 8 * j);
+                    } else if ((part >> 1) == h) {           // box part & 1 holds my 32 fp32 columns = 8 chunks of 4
+                        uint8_t *rowp = s_lin + (part & 1) * kFuBoxF32 + row_in_cta * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4 *>(rowp + ((j ^ sw) << 4)) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (kFuWarpArrive ? lane == 0 : true) mbar_arrive(lin_staged);
+                }
+                continue;
+            }
+            // GRU tile: two passes of 32 units through the staging buffers
+            for (int c = 0; c < 2; ++c, ++pc) {
                 const int buf = (int) (pc & 1);
                 uint8_t *f32_row = s_f32 + buf * kFuBoxF32 + row_in_cta * 128;
                 uint8_t *b16_row = s_b16 + buf * kFuBoxB16 + row_in_cta * 64;
-                const int cu = c * 32 + part * 8;            // first of my 8 columns (units / outputs) inside the tile
-                float out[8];
-                if (mode == kTcGru) {
-                    float anx[8], ar[8], az[8], anh[8], hp[8];
-                    tmem_ld8(t0 + 0 + cu, anx);
-                    tmem_ld8(t0 + 64 + cu, ar);
-                    tmem_ld8(t0 + 128 + cu, az);
-                    tmem_ld8(t0 + 192 + cu, anh);
-                    mbar_wait(&box_ready[buf], (pc >> 1) & 1);   // h(t-1) of this pass has landed
+                const int cu = c * 32 + part * 8;            // first of my 8 units inside the tile
+                float anx[8], ar[8], az[8], anh[8], hp[8], out[8];
+                tmem_ld8(t0 + 0 + cu, anx);
+                tmem_ld8(t0 + 64 + cu, ar);
+                tmem_ld8(t0 + 128 + cu, az);
+                tmem_ld8(t0 + 192 + cu, anh);
+                mbar_wait(&box_ready[buf], (pc >> 1) & 1);   // h(t-1) of this pass has landed
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const float4 v = *reinterpret_cast<const float4 *>(f32_row + (((part * 2 + q) ^ sw) << 4));
-                        hp[4 * q] = v.x; hp[4 * q + 1] = v.y; hp[4 * q + 2] = v.z; hp[4 * q + 3] = v.w;
-                    }
-                    tmem_ld_wait();
-                    if (te == 0) KTRACE(it * 48 + 8 + c * 2);
-                    tmem_zero8(t0 + 192 + cu);                   // n_h columns must be zero when the buffer is reused
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        // r = 1/(1+er), z = 1/(1+ez) share one reciprocal: 5 MUFU ops per unit.  Arguments are clamped so that
-                        // (1+er)(1+ez) cannot overflow: sigmoid(-30) is already 9e-14.
-                        const float er = ex2_approx(fminf(fmaf(ar[i], -kL2e, sb[64 + cu + i]), 43.0f));
-                        const float ez = ex2_approx(fminf(fmaf(az[i], -kL2e, sb[128 + cu + i]), 43.0f));
-                        const float pr = 1.0f + er, pz = 1.0f + ez;
-                        const float ip = rcp_approx(pr * pz);
-                        const float rg = pz * ip, zg = pr * ip;
-                        const float a = fmaf(rg, anh[i] + sb[192 + cu + i], anx[i] + sb[cu + i]);
-                        const float ng = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(a * (2.0f * kL2e))), 1.0f);   // tanh(a)
-                        out[i] = fmaf(zg, hp[i] - ng, ng);       // (1 - z) n + z h
-                    }
-                    if (c == 1) tmem_st_wait();
-                } else {
-                    tmem_ld8(t0 + cu, out);
-                    mbar_wait(&box_ready[buf], (pc >> 1) & 1);   // the stores of two passes ago have read the buffer
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float v = out[i] + sb[cu + i];
-                        out[i] = mode == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
-                    }
+                for (int q = 0; q < 2; ++q) {
+                    const float4 v = *reinterpret_cast<const float4 *>(f32_row + (((part * 2 + q) ^ sw) << 4));
+                    hp[4 * q] = v.x; hp[4 * q + 1] = v.y; hp[4 * q + 2] = v.z; hp[4 * q + 3] = v.w;
                 }
-                if (c + 1 == npass) {                        // last TMEM access of this tile: hand the buffer back
+                tmem_ld_wait();
+                if (te == 0) KTRACE(it * 48 + 8 + c * 2);
+                tmem_zero8(t0 + 192 + cu);                   // n_h columns must be zero when the buffer is reused
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    // r = 1/(1+er), z = 1/(1+ez) share one reciprocal: 5 MUFU ops per unit.  Arguments are clamped so that
+                    // (1+er)(1+ez) cannot overflow: sigmoid(-30) is already 9e-14.
+                    const float er = ex2_approx(fminf(fmaf(ar[i], -kL2e, sb[64 + cu + i]), 43.0f));
+                    const float ez = ex2_approx(fminf(fmaf(az[i], -kL2e, sb[128 + cu + i]), 43.0f));
+                    const float pr = 1.0f + er, pz = 1.0f + ez;
+                    const float ip = rcp_approx(pr * pz);
+                    const float rg = pz * ip, zg = pr * ip;
+                    const float a = fmaf(rg, anh[i] + sb[192 + cu + i], anx[i] + sb[cu + i]);
+                    const float ng = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(a * (2.0f * kL2e))), 1.0f);   // tanh(a)
+                    out[i] = fmaf(zg, hp[i] - ng, ng);       // (1 - z) n + z h
+                }
+                if (c == 1) {                                // last TMEM access of this tile: hand the buffer back
+                    tmem_st_wait();
                     tc_fence_before();
                     if (te == 0) KTRACE(it * 48 + 6);
-                    mbar_arrive_cluster(empty_leader[ab]);
+                    __syncwarp();
+                    if (kFuWarpArrive ? lane == 0 : true) mbar_arrive_cluster(empty_leader[ab]);
                 }
-                if (mode != kTcEnc) {                        // fp32 box (GRU: h(t) replaces h(t-1) in place; decoder: the mask)
 #pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        *reinterpret_cast<float4 *>(f32_row + (((part * 2 + q) ^ sw) << 4)) =
-                            make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
-                }
-                if (mode != kTcDec) *reinterpret_cast<uint4 *>(b16_row + part * 16) = pack_bf16x8(out);
+                for (int q = 0; q < 2; ++q)                  // h(t) replaces h(t-1) in place
+                    *reinterpret_cast<float4 *>(f32_row + (((part * 2 + q) ^ sw) << 4)) =
+                        make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+                *reinterpret_cast<uint4 *>(b16_row + part * 16) = pack_bf16x8(out);
                 fence_proxy_async();                         // my smem writes -> visible to the TMA engine
-                mbar_arrive(&staged[buf]);                   // the state warp stores the pass once all 512 threads are here
+                __syncwarp();
+                if (kFuWarpArrive ? lane == 0 : true) mbar_arrive(&staged[buf]);    // the state warp stores the pass once everybody is here
             }
         }
     }
@@ -525,13 +613,13 @@ static bool fu_plan_create(const TcPlan *tc, FuPlan **out, std::string *why) {
                 sg.bias0 = m.enc_b;
                 put(kMapA0, m.feat, Bp, kBins, kFuARows);
                 put(kMapB0, m.enc_w, H, kBins, kFuLinN / 2);
-                put(kMapHb, m.e, Bp, H, kTcBlockM, false, true);
+                put(kMapHn, m.e, Bp, H, kTcBlockM);                  // store map: boxes of 64 bf16 columns x 128 rows, 128B swizzle
             } else if (s == nseg - 1) {                    // decoder: mask = sigmoid(h_{L-1}(t) W_dec^T + b)
                 sg.mode = kTcDec; sg.n_ctiles = kBins / kFuLinN / kFuPN; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 1;
                 sg.bias0 = m.dec_b;
                 put(kMapA0, m.hb[nxt] + (L - 1) * LBH, Bp, H, kFuARows);
                 put(kMapB0, m.dec_w, kBins, H, kFuLinN / 2);
-                put(kMapHn, m.mask, Bp, kBins, kTcBlockM, true);
+                put(kMapHn, m.mask, Bp, kBins, kTcBlockM, true);    // store map: boxes of 32 fp32 columns x 128 rows, 128B swizzle
             } else {                                       // GRU layer l
                 const size_t l = s - 1;
                 sg.mode = kTcGru; sg.n_ctiles = m.H / kGruUnits / kFuPN; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 2;
@@ -565,7 +653,7 @@ static bool fu_plan_create(const TcPlan *tc, FuPlan **out, std::string *why) {
     {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned) (kFuCluster * tc->num_sms));
-        cfg.blockDim = dim3(kTcThreads);
+        cfg.blockDim = dim3(kFuThreads);
         cfg.dynamicSmemBytes = (size_t) kFuSmemBytes;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -585,7 +673,7 @@ static int fu_masknet_step(FuPlan *f, int cur, cudaStream_t st) {
     FuArgs &a = f->args[cur];
     a.epoch = ++f->epoch;
     const int clusters = a.total_tiles < f->max_clusters ? a.total_tiles : f->max_clusters;
-    launch_pdl(true, tc_fused_kernel, dim3((unsigned) (kFuCluster * clusters)), dim3(kTcThreads), (size_t) kFuSmemBytes, st, a);
+    launch_pdl(true, tc_fused_kernel, dim3((unsigned) (kFuCluster * clusters)), dim3(kFuThreads), (size_t) kFuSmemBytes, st, a);
     return 1;
 }
 

@@ -9,7 +9,8 @@ import koala_b200 as kb
 from koala_b200 import spec
 m = "gpurun_out/r.kpv"; os.makedirs("gpurun_out", exist_ok=True); spec.save_model(m, spec.random_model())
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-eng = kb.BatchKoala(n, model_path=m, precision="bf16")
+lib = os.path.abspath(sys.argv[2]) if len(sys.argv) > 2 else None     # a build with -DKOALA_FU_TRACE=1 (python -m koala_b200._build -DKOALA_FU_TRACE=1 -o<path>)
+eng = kb.BatchKoala(n, model_path=m, precision="bf16", library_path=lib)
 pcm = (np.random.default_rng(0).standard_normal((n, 4, 256)) * 2000).astype(np.int16)
 eng.process(pcm)
 tr = eng.debug_read("trace", (2, 1024), np.int64)
