@@ -36,7 +36,10 @@ namespace koala {
 #endif
 constexpr int kFuStages = KOALA_FU_STAGES;
 constexpr int kFuStageBytes = kTcABytes + (kGruRows / 2) * 128;   // 28 KB: A [128][64] + B up to [96][64] bf16 (linear tiles: 64 rows)
-constexpr int kFuPN = 2;                                          // CTA pairs per cluster (neighbouring n tiles of one m tile)
+#ifndef KOALA_FU_PN
+#define KOALA_FU_PN 1
+#endif
+constexpr int kFuPN = KOALA_FU_PN;                                       // CTA pairs per cluster (neighbouring n tiles of one m tile)
 constexpr int kFuCluster = 2 * kFuPN;
 constexpr int kFuARows = kTcBlockM / kFuPN;                       // rows of A each CTA fetches and multicasts
 constexpr int kFuLinN = 128;                                      // outputs per linear pair tile
@@ -172,11 +175,13 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         const int par = is_a ? warp : warp - 3;             // my k-block parity
         if (is_a) pdl_wait();
         int stage = par, phase = 0;                         // kStages is even: a warp stays on the stages of its parity
-        const uint16_t mask_a = (uint16_t) ((1u << rank) | (1u << (2 + rank)));   // same position in both pairs
+        uint16_t mask_a = 0;                                 // same position in every pair of the cluster
+#pragma unroll
+        for (int j = 0; j < kFuPN; ++j) mask_a |= (uint16_t) (1u << (2 * j + rank));
         auto arow_of = [&](int m) { return m * kTcPairM + (int) rank * kTcBlockM + qn * kFuARows; };   // first of the 64 rows I fetch
         int pit = 0;
-        unsigned seen = 0;              // the next tile's dependency counter, sampled one tile early
-        bool seen_valid = false;
+        unsigned seen = 0, seen_this = 0;   // the next tile's dependency counter, sampled one tile early
+        bool seen_valid = false, seen_valid_this = false;
         for (int g = cluster_id; g < total; g += num_clusters, ++pit) {
             const FuTile t = fu_decode(args, g);
             const FuSeg &sg = args.seg[t.s];
@@ -186,41 +191,43 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             const int brows = gru ? kGruRows / 2 : kFuLinN / 2;         // weight rows each CTA of the pair holds
             const uint32_t pair_tx = 2u * (uint32_t) (kTcABytes + brows * 128);
             if (warp == 0 && lane == 0) KTRACE(pit * 48 + 0);
-            if (is_a && sg.dep >= 0) {
-                // the rows of my m tile are written by every n tile of the previous segment: wait until all those CTAs have
-                // signalled (their TMA stores completed before the release).  The counter of this tile was already sampled
-                // during the previous tile (`seen`), so in the steady state nothing is waited for here.  The poll is a relaxed
-                // L1-bypassing load: the TMA unit reads through L2, where the signalled rows already are, and an acquire or a
-                // proxy fence in this thread would wait for its own outstanding TMA loads (~2 k cycles per tile, measured).
-                const unsigned target = args.epoch * sg.dep_per_step;
-                if ((int) (seen - target) < 0 || !seen_valid) {
-                    const unsigned *ctr = args.counters + (size_t) sg.dep * args.num_m_tiles + t.m;
-#ifdef KOALA_FU_POLL_ACQUIRE
-                    while ((int) (ld_acquire_gpu(ctr) - target) < 0) __nanosleep(40);
-                    fence_proxy_async_all();
-#else
-                    while ((int) (ld_relaxed_gpu(ctr) - target) < 0) __nanosleep(40);
-#endif
-                }
-            }
+            bool dep_pending = is_a && sg.dep >= 0;
+            seen_valid_this = seen_valid; seen_this = seen;
             seen_valid = false;
-            if (warp == 0 && lane == 0) KTRACE(pit * 48 + 12);
             for (int kb = par; kb < num_kb; kb += 2) {
+                // GRU tiles take their h(t-1) part FIRST: it does not depend on the previous segment, so the dependency wait
+                // below only holds the second half of the k loop and is usually over by the time it is reached
+                const bool second = gru && kb < sg.kb_per_part;      // second operand pair (A1 / B1) = the h part
+                if (dep_pending && !second) {
+                    // the rows of my m tile are written by every n tile of the previous segment: wait until all those CTAs have
+                    // signalled (their stores completed before the release).  The counter was already sampled during the
+                    // previous tile, so in the steady state nothing is waited for here.  The fast path is a relaxed
+                    // L1-bypassing load: the TMA unit reads through L2, where the signalled rows already are, and an acquire
+                    // or a proxy fence in this thread waits for its own outstanding TMA loads (~2 k cycles per tile, measured).
+                    const unsigned target = args.epoch * sg.dep_per_step;
+                    if (!seen_valid_this || (int) (seen_this - target) < 0) {
+                        const unsigned *ctr = args.counters + (size_t) sg.dep * args.num_m_tiles + t.m;
+                        while ((int) (ld_acquire_gpu(ctr) - target) < 0) __nanosleep(40);
+                        fence_proxy_async_all();
+                    }
+                    dep_pending = false;
+                    if (warp == 0 && lane == 0) KTRACE(pit * 48 + 12);
+                }
                 mbar_wait(&empty_bar[stage], phase ^ 1);     // slot free in every CTA of the cluster
                 if (is_a && lane == 0) KTRACE(pit * 48 + 16 + kb);
                 const bool elected = elect_one();
                 if (elected && is_a && rank == 0) mbar_expect_tx(&full_bar[stage], pair_tx);
                 const uint32_t full_leader = map_to_cta(&full_bar[stage], leader);
                 uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kTcABytes;
-                const bool second = kb >= sg.kb_per_part;
-                const int kc = (second ? kb - sg.kb_per_part : kb) * kTcBlockK;
+                const int kc = (kb >= sg.kb_per_part ? kb - sg.kb_per_part : kb) * kTcBlockK;
                 if (!elected) {
                 } else if (is_a) {
 #ifdef KOALA_FU_NO_MC      // diagnostic: every CTA fetches both 64-row pieces of its A block itself
                     for (int j = 0; j < kFuPN; ++j)
                         tma_load_2d_pair(maps + (second ? kMapA1 : kMapA0), full_leader, sa + j * kFuARows * 128, kc, t.m * kTcPairM + (int) rank * kTcBlockM + j * kFuARows);
 #else
-                    tma_load_2d_pair_mc(maps + (second ? kMapA1 : kMapA0), full_leader, sa + qn * kFuARows * 128, kc, arow_of(t.m), mask_a);
+                    if (kFuPN > 1) tma_load_2d_pair_mc(maps + (second ? kMapA1 : kMapA0), full_leader, sa + qn * kFuARows * 128, kc, arow_of(t.m), mask_a);
+                    else tma_load_2d_pair(maps + (second ? kMapA1 : kMapA0), full_leader, sa, kc, arow_of(t.m));
 #endif
                 } else {
                     tma_load_2d_pair(maps + (second ? kMapB1 : kMapB0), full_leader, sb, kc, n * 2 * brows + (int) rank * brows);
@@ -259,7 +266,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
     } else if (warp == 2) {
         // ===================================================== MMA issuer (one thread of the leader CTA drives both SMs)
         if (rank == 0) {
-            int stage = 0, phase = 0, it = 0;
+            int it = 0;
+            unsigned kb_total = 0;           // k-blocks issued so far: every lane derives the pipeline position from it
             const uint64_t adesc0 = make_sw128_desc(smem_u32(smem)), bdesc0 = make_sw128_desc(smem_u32(smem) + kTcABytes);
             for (int g = cluster_id; g < total; g += num_clusters, ++it) {
                 const FuTile t = fu_decode(args, g);
@@ -272,23 +280,31 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 tc_fence_after();
                 if (lane == 0) KTRACE(it * 48 + 2);
                 const uint32_t d = tmem_base + ab * kTcAccCols;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    if (lane == 0) KTRACE(it * 48 + 32 + kb);
-                    const bool hpart = gru && kb >= kbp;   // GRU h-part: columns [r | z | n_h], always accumulating
-                    const uint32_t dk = hpart ? d + kGruUnits : d, acc0 = hpart ? 1u : (uint32_t) (kb != 0);
-                    if (elect_one()) {
-                        const uint64_t so = (uint64_t) ((stage * kStageBytes) >> 4);
+                // The whole k loop runs in ONE elected lane: every instruction between two k-blocks (barrier test, descriptor
+                // arithmetic, moves into uniform registers) is serial latency of this thread and shows up one-for-one in the
+                // k-block time, so nothing is re-elected, re-synchronised or re-selected per k-block, and the loop is split by
+                // operand part to keep its body branch-free.  GRU: the h part comes first and initialises columns [r | z | n_h];
+                // the x part accumulates into [n_x | r | z], whose n_x columns the epilogue left zeroed.
+                int stage = (int) (kb_total % kStages), phase = (int) ((kb_total / kStages) & 1);
+                kb_total += (unsigned) num_kb;
+                if (elect_one()) {
+                    for (int part = 0; part < sg.parts; ++part) {
+                        const uint32_t dk = (gru && part == 0) ? d + kGruUnits : d;
+                        const uint32_t first = (gru && part == 1) ? 1u : 0u;    // linear tiles and the GRU h part start from zero
+                        for (int kb = 0; kb < kbp; ++kb) {
+                            mbar_wait(&full_bar[stage], phase);
+                            tc_fence_after();
+                            KTRACE(it * 48 + 32 + part * kbp + kb);
+                            const uint64_t so = (uint64_t) ((stage * kStageBytes) >> 4);
 #pragma unroll
-                        for (int k = 0; k < kTcBlockK / 16; ++k)    // +32 B per 16-element k-step
-                            umma_bf16_pair(dk, adesc0 + so + 2 * k, bdesc0 + so + 2 * k, idesc, k == 0 ? acc0 : 1u);
-                        umma_commit_pair(&empty_bar[stage], all_mask);   // partners multicast into my slots, so everyone must know
+                            for (int k = 0; k < kTcBlockK / 16; ++k)    // +32 B per 16-element k-step
+                                umma_bf16_pair(dk, adesc0 + so + 2 * k, bdesc0 + so + 2 * k, idesc, (kb | k) != 0 ? 1u : first);
+                            umma_commit_pair(&empty_bar[stage], all_mask);   // partners multicast into my slots, so everyone must know
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
                     }
-                    __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    umma_commit_pair(&tmem_full[ab], pair_mask);
                 }
-                if (elect_one()) umma_commit_pair(&tmem_full[ab], pair_mask);
                 __syncwarp();
                 if (lane == 0) KTRACE(it * 48 + 3);
             }
@@ -406,11 +422,11 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         const int quarter = warp & 3, part = (warp - 5) >> 2, te = threadIdx.x - 160;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
         uint32_t empty_leader[2] = {map_to_cta(&tmem_empty[0], leader), map_to_cta(&tmem_empty[1], leader)};
-        // hand both buffers to the MMA issuer for the first time, with the GRU n_h columns cleared (linear tiles never touch them)
+        // hand both buffers to the MMA issuer for the first time, with the GRU n_x columns cleared (linear tiles start from zero anyway)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            tmem_zero8(lane_base + b * kTcAccCols + 192 + part * 16);
-            tmem_zero8(lane_base + b * kTcAccCols + 192 + part * 16 + 8);
+            tmem_zero8(lane_base + b * kTcAccCols + part * 16);
+            tmem_zero8(lane_base + b * kTcAccCols + part * 16 + 8);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -459,6 +475,10 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tmem_ld8(t0 + part * 32 + 8 * j, *reinterpret_cast<float(*)[8]>(acc + 8 * j));
                 tmem_ld_wait();
+                asm volatile("bar.sync 2, %0;" ::"n"(kTcEpiThreads) : "memory");   // everybody has read columns 0..63 ...
+                tmem_zero8(t0 + part * 16);                  // ... which a GRU tile that takes this buffer next expects zeroed (its n_x)
+                tmem_zero8(t0 + part * 16 + 8);
+                tmem_st_wait();
                 tc_fence_before();
                 if (te == 0) KTRACE(it * 48 + 6);
                 __syncwarp();
@@ -507,7 +527,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 }
                 tmem_ld_wait();
                 if (te == 0) KTRACE(it * 48 + 8 + c * 2);
-                tmem_zero8(t0 + 192 + cu);                   // n_h columns must be zero when the buffer is reused
+                tmem_zero8(t0 + cu);                         // n_x columns must be zero when the next GRU tile's x part accumulates into them
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     // r = 1/(1+er), z = 1/(1+ez) share one reciprocal: 5 MUFU ops per unit.  Arguments are clamped so that

@@ -14,8 +14,11 @@
 
 namespace koala {
 
+#ifndef KOALA_STFT_CTAS
+#define KOALA_STFT_CTAS 6
+#endif
 constexpr int kStftWarps = 4;         // warps (= streams in flight) per CTA
-constexpr int kStftCtasPerSm = 6;     // 24 resident warps per SM: at most 80 registers per thread
+constexpr int kStftCtasPerSm = KOALA_STFT_CTAS;     // resident CTAs per SM the register budget is sized for
 
 template <typename FeatT> __device__ __forceinline__ void store_feat(FeatT *dst, float f);
 template <> __device__ __forceinline__ void store_feat<float>(float *dst, float f) { *dst = f; }
