@@ -12,7 +12,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 300
 m = "gpurun_out/r.kpv"; os.makedirs("gpurun_out", exist_ok=True); spec.save_model(m, spec.random_model())
 eng = kb.BatchKoala(n, model_path=m, precision="bf16", library_path=lib_path)
-ring = 16
+ring = int(os.environ.get("RING", "64"))      # frames per stream resident in HBM: 64 = bench.py (512 MiB in + out, larger than L2)
 pcm = torch.from_numpy((np.random.default_rng(0).standard_normal((ring, n, 256)) * 2000).astype(np.int16)).cuda()
 out = torch.empty_like(pcm)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
