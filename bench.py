@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--workload", default="cfg4_8192_per_gpu_bf16", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
     ap.add_argument("--ring-frames", type=int, default=64, help="distinct input frames per stream kept in HBM")
-    ap.add_argument("--e2e-steps", type=int, default=64)
+    ap.add_argument("--e2e-steps", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -279,29 +279,36 @@ def main():
     prof = eng.profile_read()
     eng.profile(False)
 
-    # ---- end to end through the public API with pinned HOST buffers: one call carries e2e_steps frames of every stream;
-    # inside it every step's 256-sample frames go host -> device and its enhanced frames device -> host (chunked, copies
-    # overlapped with compute by the library's ingest path).  Timed by wall clock around the synchronous call.
+    # ---- end to end through the public API with pinned HOST buffers: one call carries e2e_steps frames of every stream in the
+    # time-major layout [steps][B][256] (a frame of every stream per 16 ms tick); inside it every step's 256-sample frames go
+    # host -> device and its enhanced frames device -> host, chunk by chunk, overlapped with compute by the library's ingest
+    # path.  Timed by wall clock around the synchronous call.
     e2e_steps = max(8, args.e2e_steps)
-    e2e_ring = min(e2e_steps, ring)
-    h_in = torch.from_numpy(np.ascontiguousarray(host_pcm[:, :e2e_ring, :])).pin_memory()
-    if e2e_ring < e2e_steps:
-        h_in = h_in.repeat(1, (e2e_steps + e2e_ring - 1) // e2e_ring, 1)[:, :e2e_steps, :].contiguous().pin_memory()
+    tm = np.ascontiguousarray(host_pcm.transpose(1, 0, 2))        # [ring][B][256]
+    h_in = torch.from_numpy(np.concatenate([tm] * ((e2e_steps + ring - 1) // ring), axis=0)[:e2e_steps]).pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
-    eng.process(h_in[:, :8, :].contiguous().pin_memory(), out=torch.empty_like(h_in[:, :8, :]).contiguous().pin_memory())   # warm-up (allocates staging)
+    eng.process(h_in[:8].contiguous().pin_memory(), out=torch.empty_like(h_in[:8]).pin_memory(), time_major=True)   # warm-up (allocates staging)
     barrier()
     t0 = time.perf_counter()
-    eng.process(h_in, out=h_out)                                  # synchronous: returns when h_out is valid
+    eng.process(h_in, out=h_out, time_major=True)                 # synchronous: returns when h_out is valid
     torch.cuda.synchronize(dev)
     e2e_s_local = time.perf_counter() - t0
     # the same thing one step per call (the latency-bound way to drive the API), for reference
-    h1_in = h_in[:, 0, :].contiguous().pin_memory()
+    h1_in = h_in[0].contiguous().pin_memory()
     h1_out = torch.empty_like(h1_in).pin_memory()
     eng.process(h1_in, out=h1_out)
     t0 = time.perf_counter()
     for i in range(20):
         eng.process(h1_in, out=h1_out)
     e2e_single_call_fps = streams * 20 / (time.perf_counter() - t0)
+    # ... and one call in the stream-major layout [B][steps][256] (pitched copies, wide output blocks)
+    s_in = torch.from_numpy(np.ascontiguousarray(h_in.numpy().transpose(1, 0, 2))).pin_memory()
+    s_out = torch.empty_like(s_in).pin_memory()
+    t0 = time.perf_counter()
+    eng.process(s_in, out=s_out)
+    torch.cuda.synchronize(dev)
+    e2e_stream_major_fps = streams * e2e_steps / (time.perf_counter() - t0)
+    del s_in, s_out
 
     # ---- reduce over ranks: SUM of units, MAX of time
     def reduce(v, op):
@@ -377,8 +384,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": streams * FRAME * 2,
                     "d2h_bytes_per_step": streams * FRAME * 2, "steps": e2e_steps,
-                    "api": "koala_b200.BatchKoala.process(pinned host tensor [B][steps][256]) -> pv_koala_batch_process, one call",
-                    "one_step_per_call_value_rank0": e2e_single_call_fps},
+                    "api": "koala_b200.BatchKoala.process(pinned host tensor [steps][B][256], time_major=True) -> "
+                           "pv_koala_batch_process_time_major, one call",
+                    "one_step_per_call_value_rank0": e2e_single_call_fps, "stream_major_call_value_rank0": e2e_stream_major_fps},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -93,6 +93,13 @@ PV_API void pv_koala_batch_delete(pv_koala_batch_t *object);
  * Host buffers: copies + compute + copy back, returns when enhanced_pcm is valid.  Device buffers: synchronous too. */
 PV_API pv_status_t pv_koala_batch_process(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm, int32_t num_frames);
 
+/* Same call with TIME-MAJOR buffers, [num_frames][num_streams][256]: frame t of every stream is one contiguous block, which
+ * is what a caller driving many pv_koala_process-style streams in lock step (one 256-sample frame per stream per 16 ms tick,
+ * /root/reference/demo/c/koala_demo_file.c:466-521 run for many files at once) has in hand.  For host buffers this is the
+ * fast path: every chunk of the ingest pipeline is one contiguous copy in each direction. */
+PV_API pv_status_t pv_koala_batch_process_time_major(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,
+                                                     int32_t num_frames);
+
 /* Device buffers only, enqueue-only: frame t of stream s at base + s * stream_stride + t * 256 samples (16-byte aligned,
  * stride % 8 == 0).  cuda_stream: a cudaStream_t passed as void* and taken literally (NULL = CUDA's legacy default stream).
  * Work is ordered on that stream like any other kernel; pv_koala_batch_synchronize waits for the whole device. */

@@ -31,6 +31,8 @@ class BatchKoala(object):
         library.pv_koala_batch_delete.restype = None
         library.pv_koala_batch_process.argtypes = [H, c_void_p, c_void_p, c_int32]
         library.pv_koala_batch_process.restype = c_int
+        library.pv_koala_batch_process_time_major.argtypes = [H, c_void_p, c_void_p, c_int32]
+        library.pv_koala_batch_process_time_major.restype = c_int
         library.pv_koala_batch_process_async.argtypes = [H, c_void_p, c_void_p, c_int32, c_int64, c_void_p]
         library.pv_koala_batch_process_async.restype = c_int
         library.pv_koala_batch_synchronize.argtypes = [H]
@@ -66,38 +68,48 @@ class BatchKoala(object):
         except Exception:
             pass
 
-    def _shape(self, shape) -> int:
+    def _shape(self, shape, time_major: bool = False) -> int:
         if len(shape) == 2:
-            shape = (shape[0], 1, shape[1])
-        if len(shape) != 3 or shape[0] != self.num_streams or shape[2] != self.frame_length:
+            shape = (1, shape[0], shape[1]) if time_major else (shape[0], 1, shape[1])
+        streams, frames = (shape[1], shape[0]) if time_major else (shape[0], shape[1])
+        if len(shape) != 3 or streams != self.num_streams or shape[2] != self.frame_length:
             raise KoalaInvalidArgumentError(
-                "expected pcm of shape [%d][frames][%d], got %s" % (self.num_streams, self.frame_length, tuple(shape)))
-        return shape[1]
+                "expected pcm of shape %s, got %s" % ("[frames][%d][%d]" % (self.num_streams, self.frame_length) if time_major else
+                                                      "[%d][frames][%d]" % (self.num_streams, self.frame_length), tuple(shape)))
+        return frames
 
-    def process(self, pcm, out=None):
-        """pcm: int16 [B][256] or [B][T][256]; numpy (host) or torch.cuda tensor (device).  Returns the same kind."""
+    def process(self, pcm, out=None, time_major: bool = False):
+        """pcm: int16 [B][256] or [B][T][256] (time_major: [T][B][256]); numpy (host), pinned torch tensor (host) or torch.cuda
+        tensor (device).  Returns the same kind and layout.  Time-major host buffers are the fast way in: every chunk of the
+        ingest pipeline is then one contiguous copy."""
+        entry = self._library.pv_koala_batch_process_time_major if time_major else self._library.pv_koala_batch_process
         if isinstance(pcm, np.ndarray):
-            frames = self._shape(pcm.shape)
+            frames = self._shape(pcm.shape, time_major)
             pcm = np.ascontiguousarray(pcm, dtype=np.int16)
             if out is None:
                 out = np.empty_like(pcm)
-            check(self._library, self._library.pv_koala_batch_process(self._handle, pcm.ctypes.data, out.ctypes.data, frames),
-                  'Processing failed')
+            check(self._library, entry(self._handle, pcm.ctypes.data, out.ctypes.data, frames), 'Processing failed')
             return out
         import torch  # device tensors (or pinned host tensors) only
         if not isinstance(pcm, torch.Tensor) or pcm.dtype != torch.int16 or not pcm.is_contiguous():
             raise KoalaInvalidArgumentError("pcm must be a contiguous int16 numpy array or torch tensor")
-        frames = self._shape(tuple(pcm.shape))
+        frames = self._shape(tuple(pcm.shape), time_major)
         if out is None:
             out = torch.empty_like(pcm)
-        if pcm.is_cuda:
+        if pcm.is_cuda and not time_major:
             stream = torch.cuda.current_stream(pcm.device).cuda_stream
             check(self._library, self._library.pv_koala_batch_process_async(
                 self._handle, pcm.data_ptr(), out.data_ptr(), frames, frames * self.frame_length, c_void_p(stream)),
                 'Processing failed')
+        elif pcm.is_cuda:
+            stream = torch.cuda.current_stream(pcm.device).cuda_stream
+            step = self.num_streams * self.frame_length * 2
+            for t in range(frames):     # one enqueue per frame: streams 256 samples apart
+                check(self._library, self._library.pv_koala_batch_process_async(
+                    self._handle, pcm.data_ptr() + t * step, out.data_ptr() + t * step, 1, self.frame_length, c_void_p(stream)),
+                    'Processing failed')
         else:
-            check(self._library, self._library.pv_koala_batch_process(self._handle, pcm.data_ptr(), out.data_ptr(), frames),
-                  'Processing failed')
+            check(self._library, entry(self._handle, pcm.data_ptr(), out.data_ptr(), frames), 'Processing failed')
         return out
 
     def synchronize(self) -> None:

@@ -100,8 +100,12 @@ Status load_model_file(const char *path, ModelHost *out, std::vector<std::string
 }
 
 // ------------------------------------------------------------------------------------------------ engine
-constexpr int kHostRing = 3;           // device staging buffers of the host ingest path
-constexpr int kHostChunkFrames = 8;    // frames per staged chunk
+constexpr int kHostRing = 3;           // device input staging buffers of the host ingest path
+constexpr int kHostOutRing = 2;        // device output staging buffers (blocks)
+constexpr int kHostChunkFrames = 8;    // frames per input chunk
+constexpr int kHostOutFrames = 32;     // frames per output block
+constexpr int kHostBlockMinFrames = 128;   // shorter calls send their output chunk by chunk
+constexpr int kHostChunkFramesTm = 4;  // frames per chunk of a time-major call
 
 struct Engine::Impl {
     cudaStream_t stream = nullptr;
@@ -122,10 +126,10 @@ struct Engine::Impl {
     void *e = nullptr;           // fp32 | bf16 [Bp][H]
     float *mask = nullptr;       // [Bp][256]
     // staging for host-buffer calls
-    int16_t *d_in[kHostRing] = {}, *d_out[kHostRing] = {};   // [B][staging_frames][256] each
-    size_t staging_frames = 0;
+    int16_t *d_in[kHostRing] = {}, *d_out[kHostOutRing] = {};   // [B][staging_frames][256] / [B][staging_out_frames][256] each
+    size_t staging_frames = 0, staging_out_frames = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    cudaEvent_t ev_in[kHostRing] = {}, ev_comp[kHostRing] = {}, ev_out[kHostRing] = {};
+    cudaEvent_t ev_in[kHostRing] = {}, ev_comp[kHostRing] = {}, ev_out[kHostOutRing] = {};
     TcPlan *tc = nullptr;        // tensor maps + packed weights of the tcgen05 path
     FuPlan *fu = nullptr;        // the fused (one launch per step) schedule over them
     uint8_t *arena = nullptr;    // bf16 path: all per-stream state in one allocation
@@ -295,9 +299,11 @@ Engine::~Engine() {
     for (void *a : p_->allocs) cudaFree(a);
     for (int i = 0; i < kHostRing; i++) {
         if (p_->d_in[i]) cudaFree(p_->d_in[i]);
-        if (p_->d_out[i]) cudaFree(p_->d_out[i]);
         if (p_->ev_in[i]) cudaEventDestroy(p_->ev_in[i]);
         if (p_->ev_comp[i]) cudaEventDestroy(p_->ev_comp[i]);
+    }
+    for (int i = 0; i < kHostOutRing; i++) {
+        if (p_->d_out[i]) cudaFree(p_->d_out[i]);
         if (p_->ev_out[i]) cudaEventDestroy(p_->ev_out[i]);
     }
     if (p_->copy_in) cudaStreamDestroy(p_->copy_in);
@@ -307,8 +313,10 @@ Engine::~Engine() {
 }
 
 Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long long stride, void *stream_,
-                              std::vector<std::string> *errors) {
-    if (!pcm || !out || frames < 0 || stride < kFrame || (stride & 7) || ((uintptr_t) pcm & 15) || ((uintptr_t) out & 15)) {
+                              std::vector<std::string> *errors, long long out_stride) {
+    if (out_stride == 0) out_stride = stride;
+    if (!pcm || !out || frames < 0 || stride < kFrame || (stride & 7) || out_stride < kFrame || (out_stride & 7) || ((uintptr_t) pcm & 15) ||
+        ((uintptr_t) out & 15)) {
         if (errors) errors->push_back("PCM buffers must be non-NULL, 16-byte aligned, with a stream stride >= 256 and a multiple of 8.");
         return kInvalidArgument;
     }
@@ -325,7 +333,7 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     const int stft_grid = std::max(1, (B + kStftWarps * stft_per_warp - 1) / (kStftWarps * stft_per_warp));
     KernelProfiler *prof = p->prof;
     for (int t = 0; t < frames; t++) {
-        PcmView v{pcm, out, stride, t};
+        PcmView v{pcm, out, stride, out_stride, t};
         const int cur = p->parity, nxt = cur ^ 1;
         if (precision_ == kFp32) {
             float *feat = (float *) p->feat, *e = (float *) p->e;
@@ -369,11 +377,21 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     return kSuccess;
 }
 
-// Host ingest path: the caller's [B][frames][256] host buffers are cut into chunks of up to
-// kHostChunkFrames frames; chunk c+1 travels host -> device and chunk c-1 device -> host on their own streams while chunk c
-// is being processed, through a ring of three device staging buffers.  With pinned host memory the copies are true DMA
-// and the call is compute-bound from the second chunk on; pageable memory still works (the copies just serialise).
-Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::vector<std::string> *errors) {
+// Host ingest path.  The caller's [B][frames][256] host buffers are cut into INPUT chunks of
+// kHostChunkFrames frames (host -> device, then computed) and OUTPUT blocks of kHostOutFrames frames (device -> host), each on
+// its own stream through rings of device staging buffers, so that chunk c+1 travels in and the previous block travels out
+// while chunk c is being processed.  The two sizes differ because of what the copy engine does under load (tools/d2h_probe.py,
+// B200, PCIe 5): both directions are pitched 2-D copies whose contiguous run is one stream's frames of the chunk; host ->
+// device keeps 51 GiB/s with 4 KB runs whatever the SMs do, device -> host drops to 31 GiB/s with 4-8 KB runs while the step's
+// kernels are running and needs >= 16 KB runs (32 frames) for 44 GiB/s.  The last block is sent chunk by chunk instead: nothing
+// competes with those copies once the compute has drained, and the call ends one chunk, not one block, after the last step.
+// Short calls (< kHostBlockMinFrames) keep chunk-sized output copies: a block would leave too late to be hidden.
+// TIME-MAJOR host buffers ([frames][B][256], what a caller that collects one frame per stream per tick has anyway) avoid the
+// problem altogether: a chunk is one contiguous range on both sides, every copy runs at ~50 GiB/s in both directions under
+// load, chunks can be short (kHostChunkFramesTm frames: 0.3 ms to fill and to drain the pipeline) and the call is bound by
+// max(compute, PCIe): 4 MiB in + 4 MiB out per step of 8192 streams is ~83 us at 47 GiB/s each way, the step itself 83 us.
+// With pinned host memory the copies are true DMA; pageable memory still works (the copies just serialise).
+Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::vector<std::string> *errors, bool time_major) {
     if (!pcm || !out || frames < 0) {
         if (errors) errors->push_back("PCM buffers must be non-NULL.");
         return kInvalidArgument;
@@ -381,19 +399,26 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
     if (frames == 0) return kSuccess;
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
-    const int Tc = frames < kHostChunkFrames ? frames : kHostChunkFrames;
-    if ((size_t) Tc > p->staging_frames) {
+    static const int chunk_env = [] { const char *e = getenv("KOALA_HOST_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : kHostChunkFrames; }();
+    static const int out_env = [] { const char *e = getenv("KOALA_HOST_OUT_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : kHostOutFrames; }();
+    const int chunk_frames = time_major ? kHostChunkFramesTm : chunk_env;
+    const int Tc = frames < chunk_frames ? frames : chunk_frames;                 // frames per input chunk
+    const int per_block = (time_major || frames < kHostBlockMinFrames) ? 1 : std::max(1, std::min(out_env, frames) / Tc);   // input chunks per output block
+    const int To = per_block * Tc;                                                // frames per output block
+    if ((size_t) Tc > p->staging_frames || (size_t) To > p->staging_out_frames) {
         for (int i = 0; i < kHostRing; i++) {
             if (p->d_in[i]) cudaFree(p->d_in[i]);
+            p->d_in[i] = nullptr;
+        }
+        for (int i = 0; i < kHostOutRing; i++) {
             if (p->d_out[i]) cudaFree(p->d_out[i]);
-            p->d_in[i] = p->d_out[i] = nullptr;
+            p->d_out[i] = nullptr;
         }
-        p->staging_frames = 0;
-        for (int i = 0; i < kHostRing; i++) {
-            KCHECK(cudaMalloc((void **) &p->d_in[i], (size_t) n_ * Tc * kFrame * sizeof(int16_t)));
-            KCHECK(cudaMalloc((void **) &p->d_out[i], (size_t) n_ * Tc * kFrame * sizeof(int16_t)));
-        }
+        p->staging_frames = p->staging_out_frames = 0;
+        for (int i = 0; i < kHostRing; i++) KCHECK(cudaMalloc((void **) &p->d_in[i], (size_t) n_ * Tc * kFrame * sizeof(int16_t)));
+        for (int i = 0; i < kHostOutRing; i++) KCHECK(cudaMalloc((void **) &p->d_out[i], (size_t) n_ * To * kFrame * sizeof(int16_t)));
         p->staging_frames = Tc;
+        p->staging_out_frames = To;
     }
     if (!p->copy_in) {
         KCHECK(cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking));
@@ -401,29 +426,50 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
         for (int i = 0; i < kHostRing; i++) {
             KCHECK(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
             KCHECK(cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
-            KCHECK(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < kHostOutRing; i++) KCHECK(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
     }
-    const size_t dpitch = (size_t) p->staging_frames * kFrame * sizeof(int16_t);   // device staging: [B][Tc][256]
-    const size_t hpitch = (size_t) frames * kFrame * sizeof(int16_t);              // host: [B][frames][256]
-    const int chunks = (frames + Tc - 1) / Tc;
+    const size_t in_pitch = (size_t) p->staging_frames * kFrame * sizeof(int16_t);        // device input staging: [B][Tc][256]
+    const size_t out_pitch = (size_t) p->staging_out_frames * kFrame * sizeof(int16_t);   // device output staging: [B][To][256]
+    const size_t hpitch = (size_t) frames * kFrame * sizeof(int16_t);                     // host: [B][frames][256]
+    const int chunks = (frames + Tc - 1) / Tc, blocks = (chunks + per_block - 1) / per_block;
     for (int c = 0; c < chunks; c++) {
-        const int buf = c % kHostRing, t0 = c * Tc, tc = frames - t0 < Tc ? frames - t0 : Tc;
-        const size_t width = (size_t) tc * kFrame * sizeof(int16_t);
-        // host -> device once the compute that last used this staging buffer is done
-        if (c >= kHostRing) KCHECK(cudaStreamWaitEvent(p->copy_in, p->ev_comp[buf], 0));
-        KCHECK(cudaMemcpy2DAsync(p->d_in[buf], dpitch, pcm + (size_t) t0 * kFrame, hpitch, width, n_, cudaMemcpyHostToDevice, p->copy_in));
-        KCHECK(cudaEventRecord(p->ev_in[buf], p->copy_in));
-        // compute once the input has landed and the previous contents of the output staging buffer have left
-        KCHECK(cudaStreamWaitEvent(p->stream, p->ev_in[buf], 0));
-        if (c >= kHostRing) KCHECK(cudaStreamWaitEvent(p->stream, p->ev_out[buf], 0));
-        Status st = process_device(p->d_in[buf], p->d_out[buf], tc, (long long) p->staging_frames * kFrame, p->stream, errors);
+        const int ib = c % kHostRing, blk = c / per_block, ob = blk % kHostOutRing, slot = c % per_block;
+        const int t0 = c * Tc, tc = frames - t0 < Tc ? frames - t0 : Tc;
+        const bool block_end = slot == per_block - 1 || c == chunks - 1, last_block = blk == blocks - 1;
+        // host -> device once the compute that last used this input buffer is done
+        if (c >= kHostRing) KCHECK(cudaStreamWaitEvent(p->copy_in, p->ev_comp[ib], 0));
+        if (time_major)
+            KCHECK(cudaMemcpyAsync(p->d_in[ib], pcm + (size_t) t0 * n_ * kFrame, (size_t) tc * n_ * kFrame * sizeof(int16_t), cudaMemcpyHostToDevice, p->copy_in));
+        else
+            KCHECK(cudaMemcpy2DAsync(p->d_in[ib], in_pitch, pcm + (size_t) t0 * kFrame, hpitch, (size_t) tc * kFrame * sizeof(int16_t), n_,
+                                     cudaMemcpyHostToDevice, p->copy_in));
+        KCHECK(cudaEventRecord(p->ev_in[ib], p->copy_in));
+        // compute once the input has landed and (first chunk of a block) the block that last used this output buffer has left
+        KCHECK(cudaStreamWaitEvent(p->stream, p->ev_in[ib], 0));
+        if (slot == 0 && blk >= kHostOutRing) KCHECK(cudaStreamWaitEvent(p->stream, p->ev_out[ob], 0));
+        Status st = kSuccess;
+        if (time_major) {       // staging buffers are [tc][B][256]: one step per frame, streams 256 samples apart
+            for (int t = 0; t < tc && st == kSuccess; t++)
+                st = process_device(p->d_in[ib] + (size_t) t * n_ * kFrame, p->d_out[ob] + (size_t) t * n_ * kFrame, 1, kFrame, p->stream, errors);
+        } else {
+            st = process_device(p->d_in[ib], p->d_out[ob] + (size_t) slot * Tc * kFrame, tc, (long long) p->staging_frames * kFrame, p->stream,
+                                errors, (long long) p->staging_out_frames * kFrame);
+        }
         if (st != kSuccess) return st;
-        KCHECK(cudaEventRecord(p->ev_comp[buf], p->stream));
-        // device -> host
-        KCHECK(cudaStreamWaitEvent(p->copy_out, p->ev_comp[buf], 0));
-        KCHECK(cudaMemcpy2DAsync(out + (size_t) t0 * kFrame, hpitch, p->d_out[buf], dpitch, width, n_, cudaMemcpyDeviceToHost, p->copy_out));
-        KCHECK(cudaEventRecord(p->ev_out[buf], p->copy_out));
+        KCHECK(cudaEventRecord(p->ev_comp[ib], p->stream));
+        // device -> host: whole blocks, except the last block, which leaves chunk by chunk
+        if (block_end || last_block) {
+            const int first = last_block ? slot : 0;                                  // first input chunk of the block in this copy
+            const int f0 = blk * To + first * Tc, nf = t0 + tc - f0;                  // frames [f0, f0 + nf) of the call
+            KCHECK(cudaStreamWaitEvent(p->copy_out, p->ev_comp[ib], 0));
+            if (time_major)
+                KCHECK(cudaMemcpyAsync(out + (size_t) f0 * n_ * kFrame, p->d_out[ob], (size_t) nf * n_ * kFrame * sizeof(int16_t), cudaMemcpyDeviceToHost, p->copy_out));
+            else
+                KCHECK(cudaMemcpy2DAsync(out + (size_t) f0 * kFrame, hpitch, p->d_out[ob] + (size_t) first * Tc * kFrame, out_pitch,
+                                         (size_t) nf * kFrame * sizeof(int16_t), n_, cudaMemcpyDeviceToHost, p->copy_out));
+            if (block_end) KCHECK(cudaEventRecord(p->ev_out[ob], p->copy_out));
+        }
     }
     KCHECK(cudaStreamSynchronize(p->copy_out));
     KCHECK(cudaStreamSynchronize(p->stream));

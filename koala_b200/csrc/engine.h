@@ -42,9 +42,9 @@ public:
     // stride a multiple of 8.  Enqueues `frames` consecutive steps on `stream` (a cudaStream_t taken literally: nullptr is
     // the legacy default stream; own_stream() is the engine's private one) and returns without synchronising.
     Status process_device(const int16_t *pcm, int16_t *out, int frames, long long stride, void *stream,
-                          std::vector<std::string> *errors);
-    // Host buffers [B][frames][256]: H2D copy, steps, D2H copy, synchronise.
-    Status process_host(const int16_t *pcm, int16_t *out, int frames, std::vector<std::string> *errors);
+                          std::vector<std::string> *errors, long long out_stride = 0 /* 0: same as stride */);
+    // Host buffers, [B][frames][256] or (time_major) [frames][B][256]: H2D copies, steps and D2H copies overlapped, synchronise.
+    Status process_host(const int16_t *pcm, int16_t *out, int frames, std::vector<std::string> *errors, bool time_major = false);
     Status reset(const int32_t *stream_ids, int n, std::vector<std::string> *errors);   // ids == nullptr: all streams
     Status synchronize(std::vector<std::string> *errors);   // waits for everything queued on the device
     void *own_stream() const;

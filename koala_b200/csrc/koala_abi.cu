@@ -343,7 +343,7 @@ static int pointer_kind(const void *p) {   // 0 host, 1 device
     return (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? 1 : 0;
 }
 
-PV_API pv_status_t pv_koala_batch_process(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm, int32_t num_frames) {
+static pv_status_t batch_process(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm, int32_t num_frames, bool time_major) {
     if (!object) return fail_null("object");
     if (!pcm) return fail_null("pcm");
     if (!enhanced_pcm) return fail_null("enhanced_pcm");
@@ -352,16 +352,30 @@ PV_API pv_status_t pv_koala_batch_process(pv_koala_batch_t *object, const int16_
     const int kin = pointer_kind(pcm), kout = pointer_kind(enhanced_pcm);
     if (kin != kout) return fail(PV_STATUS_INVALID_ARGUMENT, {tag(kCodeGeneric, "`pcm` and `enhanced_pcm` must both be host or both be device memory.")});
     std::vector<std::string> errs;
-    Status st;
+    Status st = koala::kSuccess;
     if (kin == 1) {
-        st = object->engine->process_device(pcm, enhanced_pcm, num_frames, (long long) num_frames * koala::kFrame,
-                                            object->engine->own_stream(), &errs);
+        if (time_major) {   // [num_frames][num_streams][256]: one step per frame, streams 256 samples apart
+            const size_t frame = (size_t) object->engine->num_streams() * koala::kFrame;
+            for (int32_t t = 0; t < num_frames && st == koala::kSuccess; t++)
+                st = object->engine->process_device(pcm + t * frame, enhanced_pcm + t * frame, 1, koala::kFrame, object->engine->own_stream(), &errs);
+        } else {
+            st = object->engine->process_device(pcm, enhanced_pcm, num_frames, (long long) num_frames * koala::kFrame,
+                                                object->engine->own_stream(), &errs);
+        }
         if (st == koala::kSuccess) st = object->engine->synchronize(&errs);
     } else {
-        st = object->engine->process_host(pcm, enhanced_pcm, num_frames, &errs);
+        st = object->engine->process_host(pcm, enhanced_pcm, num_frames, &errs, time_major);
     }
     if (st != koala::kSuccess) return fail_engine(st, errs);
     return PV_STATUS_SUCCESS;
+}
+
+PV_API pv_status_t pv_koala_batch_process(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm, int32_t num_frames) {
+    return batch_process(object, pcm, enhanced_pcm, num_frames, false);
+}
+
+PV_API pv_status_t pv_koala_batch_process_time_major(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm, int32_t num_frames) {
+    return batch_process(object, pcm, enhanced_pcm, num_frames, true);
 }
 
 PV_API pv_status_t pv_koala_batch_process_async(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,

@@ -70,11 +70,12 @@ struct KernelProfiler {
     }
 };
 
-// Where one step's PCM lives: frame t of stream s starts at pcm + s * stride + t * 256 (samples).
+// Where one step's PCM lives: frame t of stream s starts at in + s * stride + t * 256 and out + s * out_stride + t * 256 (samples).
 struct PcmView {
     const int16_t *in;
     int16_t *out;
-    long long stride;   // samples between consecutive streams
+    long long stride;       // samples between consecutive streams of `in`
+    long long out_stride;   // ... of `out` (differs only inside the host ingest path, whose output blocks are wider)
     int t;              // frame index inside the caller's buffer
 };
 

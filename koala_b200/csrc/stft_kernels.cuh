@@ -159,7 +159,7 @@ backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const f
         warp_fft256<true>(z, c, lane);
 
         // z[j] = 256 (y[2p] + i y[2p+1]), p = lane + 32 j.  j < 4: first half -> output; j >= 4: second half -> new OLA tail.
-        uint32_t *out32 = reinterpret_cast<uint32_t *>(v.out + (size_t) s * v.stride + (size_t) v.t * kFrame);
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(v.out + (size_t) s * v.out_stride + (size_t) v.t * kFrame);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 w = window_pair(we, wo, j);

@@ -149,6 +149,7 @@ def test_batch_extension_argument_checks(lib, random_model_path):
         (lambda: lib.pv_koala_batch_init(random_model_path.encode(), None, 4, b"bf16", byref(b)), "device"),
         (lambda: lib.pv_koala_batch_init(random_model_path.encode(), b"gpu", 4, b"bf16", None), "object"),
         (lambda: lib.pv_koala_batch_process(None, buf, buf, 1), "object"),
+        (lambda: lib.pv_koala_batch_process_time_major(None, buf, buf, 1), "object"),
         (lambda: lib.pv_koala_batch_process_async(None, buf, buf, 1, c_int64(256), None), "object"),
         (lambda: lib.pv_koala_batch_synchronize(None), "object"),
         (lambda: lib.pv_koala_batch_reset(None, None, 0), "object"),

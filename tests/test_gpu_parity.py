@@ -97,6 +97,29 @@ def test_state_carry_reset_and_subset_reset(library_path, random_model_path, pre
     eng.delete()
 
 
+def test_long_host_call_layouts_agree(library_path, random_model_path):
+    """A 140-frame host call exercises the ingest pipeline's output blocks (32-frame blocks, a short last block, a 4-frame last
+    chunk); the time-major entry point (host and device buffers) and frame-by-frame calls must give the same samples."""
+    import torch
+    n, frames = 6, 140
+    pcm = synth_pcm(n, frames, seed=5)
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    whole = eng.process(pcm).copy()
+    eng.reset()
+    stepped = np.stack([eng.process(np.ascontiguousarray(pcm[:, t, :])) for t in range(frames)], axis=1)
+    assert (stepped == whole).all()
+    tm = np.ascontiguousarray(pcm.transpose(1, 0, 2))
+    eng.reset()
+    assert (eng.process(tm, time_major=True).transpose(1, 0, 2) == whole).all()
+    eng.reset()
+    d_out = eng.process(torch.from_numpy(tm).cuda(), time_major=True)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().numpy().transpose(1, 0, 2) == whole).all()
+    with pytest.raises(kb.KoalaInvalidArgumentError):
+        eng.process(pcm, time_major=True)                           # wrong layout for the entry point
+    eng.delete()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_edge_inputs(library_path, random_model_path, precision):
     n = 4
