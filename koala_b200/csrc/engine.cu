@@ -19,7 +19,6 @@
 
 #include "koala_common.cuh"
 #include "masknet_fp32.cuh"
-#include "masknet_tc.cuh"
 #include "masknet_fused.cuh"
 #include "stft_kernels.cuh"
 
@@ -130,8 +129,7 @@ struct Engine::Impl {
     size_t staging_frames = 0, staging_out_frames = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[kHostRing] = {}, ev_comp[kHostRing] = {}, ev_out[kHostOutRing] = {};
-    TcPlan *tc = nullptr;        // tensor maps + packed weights of the tcgen05 path
-    FuPlan *fu = nullptr;        // the fused (one launch per step) schedule over them
+    FuPlan *fu = nullptr;        // tcgen05 path: packed weights, tensor maps and the tile schedule of the fused mask-estimator kernel
     uint8_t *arena = nullptr;    // bf16 path: all per-stream state in one allocation
     size_t arena_bytes = 0;
     KernelProfiler *prof = nullptr;
@@ -268,12 +266,7 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             tm.feat = (__nv_bfloat16 *) p->feat; tm.e = (__nv_bfloat16 *) p->e; tm.mask = p->mask;
             for (int i = 0; i < 2; i++) { tm.h[i] = p->h[i]; tm.hb[i] = p->hb[i]; }
             std::string why;
-            if (!tc_plan_create(tm, &p->tc, &why)) {
-                errors->push_back("Failed to set up the tensor-core mask path: " + why);
-                return kRuntimeError;
-            }
-            const char *fe = getenv("KOALA_TC_FUSED");
-            if (!(fe && fe[0] == '0') && !fu_plan_create(p->tc, &p->fu, &why)) {
+            if (!fu_plan_create(tm, &p->fu, &why)) {
                 errors->push_back("Failed to set up the tensor-core mask path: " + why);
                 return kRuntimeError;
             }
@@ -294,7 +287,6 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     if (p_->stream) cudaStreamSynchronize(p_->stream);
     if (p_->fu) fu_plan_destroy(p_->fu);
-    if (p_->tc) tc_plan_destroy(p_->tc);
     delete p_->prof;
     for (void *a : p_->allocs) cudaFree(a);
     for (int i = 0; i < kHostRing; i++) {
@@ -359,13 +351,9 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
             launch_pdl(true, frontend_kernel<__nv_bfloat16>, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->tail, p->spec,
                                                                                   (__nv_bfloat16 *) p->feat, p->tables);
             if (prof) prof->end(st);
-            if (p->fu) {
-                if (prof) prof->begin(kKernMasknet, st);
-                launches_ += 1 + fu_masknet_step(p->fu, cur, st);
-                if (prof) prof->end(st);
-            } else {
-                launches_ += 1 + tc_masknet_step(p->tc, cur, st, prof);
-            }
+            if (prof) prof->begin(kKernMasknet, st);
+            launches_ += 1 + fu_masknet_step(p->fu, cur, st);
+            if (prof) prof->end(st);
         }
         if (prof) prof->begin(kKernBackend, st);
         launch_pdl(precision_ == kBf16, backend_kernel, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->spec, p->mask, p->ola, p->tables);
@@ -579,7 +567,6 @@ Status Engine::debug_read(const char *name, void *dst, size_t bytes, std::vector
     else if (nm == "ola") { src = p->ola; avail = B * kFrame * 4; }
     else if (nm == "tail") { src = p->tail; avail = B * kFrame * 2; }
     else if (nm == "trace" && p->fu && p->fu->trace) { src = p->fu->trace; avail = 2048 * sizeof(long long); }
-    else if (nm == "trace" && p->tc && p->tc->trace) { src = p->tc->trace; avail = 1024 * sizeof(long long); }
     else if (nm.size() == 2 && nm[0] == 'h' && nm[1] >= '0' && nm[1] < '0' + p->L) {
         src = p->h[p->parity] + (size_t) (nm[1] - '0') * Bp * H;   // h(t) of the last finished step
         avail = B * H * 4;

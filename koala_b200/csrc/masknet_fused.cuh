@@ -1,25 +1,34 @@
 // koala_b200 -- mask estimator, tensor-core path: ONE persistent kernel per step for encoder -> GRU layers -> decoder.
 //
 // Middle stage of `pv_koala_process` (/root/reference/include/pv_koala.h:65-80), batched over the stream dimension
-// (BASELINE.json configs[2..4]).  The building blocks are those of masknet_tc.cuh (bf16 operands staged by TMA into
+// (BASELINE.json configs[2..4]).  The building blocks are those of tcgen05_common.cuh (bf16 operands staged by TMA into
 // 128B-swizzled shared memory, tcgen05.mma.cta_group::2 accumulating fp32 in TMEM, gate math fused into the epilogue);
-// what changes is the schedule.  Launching the four GEMM stages as separate kernels cost, per launch, ~10 k cycles before
-// the first MMA (dependent-launch wait, cold operand pipeline) and ~7 k cycles after the last one (final epilogue), a third
-// of a GRU launch and most of an encoder / decoder launch (clock64 timelines in profiles/).  Here every stage is a SEGMENT
-// of one global list of cluster tiles
+// this file is the schedule.  Launching the four GEMM stages as separate kernels cost, per launch, ~10 k cycles before the
+// first MMA (dependent-launch wait, cold operand pipeline) and ~7 k cycles after the last one (final epilogue): a third of
+// a GRU launch and most of an encoder / decoder launch (profiles/r01_step_summary.md).  Here every stage is a SEGMENT of
+// one global list of pair tiles
 //     [encoder tiles | GRU layer 0 tiles | ... | GRU layer L-1 tiles | decoder tiles],  each segment ordered m-major,
-// walked round-robin by persistent 4-CTA clusters (two CTA pairs on neighbouring n tiles, activations multicast).  A tile
-// of segment s + 1 needs the rows of its m tile from ALL n tiles of segment s: every CTA bumps a per-(segment, m tile)
-// counter in global memory once its output stores have completed, and the activation producers of a dependent tile spin on
-// that counter before their first load.  Tiles are taken in list order, so a tile only ever waits for tiles that started
-// earlier: no deadlock as long as the grid is co-resident (it is sized by cudaOccupancyMaxActiveClusters).  Counters are
-// never reset: launch number `epoch` waits for epoch * (increments per step).
+// walked round-robin by persistent CTA pairs (2-CTA clusters on all 148 SMs).  A tile of segment s + 1 needs the rows of its
+// m tile from ALL n tiles of segment s: every CTA bumps a per-(segment, m tile) counter in global memory once its output
+// stores have completed, and the activation producers of a dependent tile test that counter before the first load that
+// needs it.  Tiles are taken in list order, so a tile only ever waits for tiles that started earlier: no deadlock as long
+// as the grid is co-resident (it is sized by cudaOccupancyMaxActiveClusters).  Counters are never reset: launch number
+// `epoch` waits for epoch * (increments per step).  GRU tiles run their h(t-1) part first -- it depends on nothing inside
+// the launch -- so the wait only ever holds the second half of a k loop.
 //
-// Warp roles (22 warps): 0,1 activation (A) producers for even / odd k-blocks, 2 TMEM allocator + MMA issuer (pair leader
-// only), 3,4 weight (B) producers, 5..20 epilogue (4 per TMEM lane quarter), 21 state warp.  The epilogue works in PASSES of
-// 32 accumulator columns (GRU tile: 2 passes of 32 units, linear tile: 4 passes of 32 outputs) through two staging buffers;
-// the state warp TMA-stores a finished pass, and re-arms its buffer for the pass two ahead: with the fp32 h(t-1) box of
-// that pass when it belongs to a GRU tile, with a plain "buffer free" arrival otherwise.
+// Warp roles (23 warps, 736 threads, 80 registers): 0,1 activation (A) producers for even / odd k-blocks, 2 TMEM allocator
+// + MMA issuer (pair leader only), 3,4 weight (B) producers (they do not wait for the previous kernel: weights are
+// constants), 5..20 epilogue (4 per TMEM lane quarter), 21 GRU state warp, 22 linear-tile store warp.
+//   GRU epilogue: two PASSES of 32 units through two staging buffers; the state warp TMA-stores a finished pass (fp32 h(t)
+//   in place of h(t-1), plus its bf16 copy) and requests the fp32 h(t-1) box of the pass two ahead into the drained buffer.
+//   Linear epilogue: the accumulator is handed back after four TMEM loads; outputs are staged in a separate 32 KB region
+//   (encoder: the CTA's whole [128][128] bf16 tile, decoder: two rounds of [128][64] fp32) and TMA-stored by warp 22.
+// Shared memory: 5 operand stages x 28 KB + 48 KB GRU staging + 32 KB linear staging + barriers / biases = 223 KB.
+//
+// What bounds it (8192 streams, B200; profiles/r01_step_summary.md): operand delivery.  Skipping every tcgen05.mma leaves
+// the kernel time unchanged (66.5 vs 65.9 us); the SMs ingest ~28 KB per k-block per ~500 cycles each (8.3 KB/clk over the
+// chip), and a GRU tile with N = 192 needs 73 B/clk/SM at full MMA rate.  TMEM (4 accumulator columns per unit, two
+// buffers) caps the tile width, hence the operand bytes per flop.
 #pragma once
 
 #include <string.h>
@@ -27,7 +36,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "masknet_tc.cuh"
+#include "tcgen05_common.cuh"
 
 namespace koala {
 
@@ -47,15 +56,10 @@ constexpr int kFuBoxF32 = kTcBlockM * 32 * 4;                     // staging box
 constexpr int kFuBoxB16 = kTcBlockM * 32 * 2;                     // staging box [128 rows][32 bf16], plain
 constexpr int kFuLinBytes = 2 * kFuBoxF32;                       // linear tiles: staging for [128][128] bf16 or [128][64] fp32 (two swizzled boxes)
 constexpr int kFuLinWarp = kTcStateWarp + 1;                      // stores the linear tiles' staged outputs
-constexpr int kFuThreads = kTcThreads + 32;
+constexpr int kFuThreads = 32 * (kFuLinWarp + 1);                 // 2 + 1 + 2 + 16 + 1 + 1 warps
 constexpr int kFuSmemBytes = kFuStages * kFuStageBytes + 2 * (kFuBoxF32 + kFuBoxB16) + kFuLinBytes + kTcTailBytes;
 constexpr int kFuMaxSegs = kMaxLayers + 2;
-#ifdef KOALA_FU_THREAD_ARRIVE
-constexpr bool kFuWarpArrive = false;
-#else
-constexpr bool kFuWarpArrive = true;     // one mbarrier arrival per epilogue warp instead of one per thread
-#endif
-constexpr int kFuArrivals = kFuWarpArrive ? kTcEpiWarps : kTcEpiThreads;
+constexpr int kFuArrivals = kTcEpiWarps;                          // epilogue barriers: one arrival per warp (after __syncwarp), not per thread
 enum FuMap : int { kMapA0 = 0, kMapA1, kMapB0, kMapB1, kMapHp, kMapHn, kMapHb, kFuMapsPerSeg };
 
 struct FuSeg {
@@ -128,8 +132,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
     const uint32_t leader = crank & ~1u;           // cluster rank of my pair's leader
     const int qn = (int) (crank >> 1);             // my pair's n tile inside the cluster tile
     const uint16_t pair_mask = (uint16_t) (3u << leader), all_mask = (uint16_t) ((1u << kFuCluster) - 1);
-    long long *trace = (args.trace != nullptr && blockIdx.x < 2) ? args.trace + blockIdx.x * 1024 : nullptr;
-    (void) trace;
+    [[maybe_unused]] long long *trace = (args.trace != nullptr && blockIdx.x < 2) ? args.trace + blockIdx.x * 1024 : nullptr;
 #ifdef KOALA_FU_TRACE      // clock64 timeline of cluster 0 (tools/gpu_trace.py builds this variant); compiled out of the product
 #define KTRACE(slot) do { if (trace && (slot) < 1024) trace[(slot)] = clock64(); } while (0)
 #else
@@ -222,13 +225,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 const int kc = (kb >= sg.kb_per_part ? kb - sg.kb_per_part : kb) * kTcBlockK;
                 if (!elected) {
                 } else if (is_a) {
-#ifdef KOALA_FU_NO_MC      // diagnostic: every CTA fetches both 64-row pieces of its A block itself
-                    for (int j = 0; j < kFuPN; ++j)
-                        tma_load_2d_pair(maps + (second ? kMapA1 : kMapA0), full_leader, sa + j * kFuARows * 128, kc, t.m * kTcPairM + (int) rank * kTcBlockM + j * kFuARows);
-#else
                     if (kFuPN > 1) tma_load_2d_pair_mc(maps + (second ? kMapA1 : kMapA0), full_leader, sa + qn * kFuARows * 128, kc, arow_of(t.m), mask_a);
                     else tma_load_2d_pair(maps + (second ? kMapA1 : kMapA0), full_leader, sa, kc, arow_of(t.m));
-#endif
                 } else {
                     tma_load_2d_pair(maps + (second ? kMapB1 : kMapB0), full_leader, sb, kc, n * 2 * brows + (int) rank * brows);
                 }
@@ -431,7 +429,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (kFuWarpArrive ? lane == 0 : true) {
+        if (lane == 0) {
             mbar_arrive_cluster(empty_leader[0]);
             mbar_arrive_cluster(empty_leader[1]);
         }
@@ -482,7 +480,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 tc_fence_before();
                 if (te == 0) KTRACE(it * 48 + 6);
                 __syncwarp();
-                if (kFuWarpArrive ? lane == 0 : true) mbar_arrive_cluster(empty_leader[ab]);
+                if (lane == 0) mbar_arrive_cluster(empty_leader[ab]);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float v = acc[i] + sb[part * 32 + i];
@@ -504,7 +502,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (kFuWarpArrive ? lane == 0 : true) mbar_arrive(lin_staged);
+                    if (lane == 0) mbar_arrive(lin_staged);
                 }
                 continue;
             }
@@ -546,7 +544,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                     tc_fence_before();
                     if (te == 0) KTRACE(it * 48 + 6);
                     __syncwarp();
-                    if (kFuWarpArrive ? lane == 0 : true) mbar_arrive_cluster(empty_leader[ab]);
+                    if (lane == 0) mbar_arrive_cluster(empty_leader[ab]);
                 }
 #pragma unroll
                 for (int q = 0; q < 2; ++q)                  // h(t) replaces h(t-1) in place
@@ -555,7 +553,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 *reinterpret_cast<uint4 *>(b16_row + part * 16) = pack_bf16x8(out);
                 fence_proxy_async();                         // my smem writes -> visible to the TMA engine
                 __syncwarp();
-                if (kFuWarpArrive ? lane == 0 : true) mbar_arrive(&staged[buf]);    // the state warp stores the pass once everybody is here
+                if (lane == 0) mbar_arrive(&staged[buf]);    // the state warp stores the pass once everybody is here
             }
         }
     }
@@ -573,7 +571,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
 // ---------------------------------------------------------------------------------------------------------------
 // host side: tensor maps and segment tables for both state parities, the dependency counters, the launch
 struct FuPlan {
-    int nseg = 0, max_clusters = 0;
+    int nseg = 0, max_clusters = 0, num_sms = 0;
+    __nv_bfloat16 *wih_p[kMaxLayers] = {}, *whh_p[kMaxLayers] = {};   // GRU weights packed per 64-unit tile (pack_gru_weights_kernel)
     unsigned epoch = 0;
     unsigned *counters = nullptr;
     CUtensorMap *d_maps[2] = {};      // [parity][nseg][kFuMapsPerSeg]
@@ -583,6 +582,10 @@ struct FuPlan {
 
 static void fu_plan_destroy(FuPlan *f) {
     if (!f) return;
+    for (int l = 0; l < kMaxLayers; l++) {
+        if (f->wih_p[l]) cudaFree(f->wih_p[l]);
+        if (f->whh_p[l]) cudaFree(f->whh_p[l]);
+    }
     if (f->counters) cudaFree(f->counters);
     for (int i = 0; i < 2; i++)
         if (f->d_maps[i]) cudaFree(f->d_maps[i]);
@@ -590,9 +593,11 @@ static void fu_plan_destroy(FuPlan *f) {
     delete f;
 }
 
-// `tc` supplies the packed GRU weights and the model / state pointers
-static bool fu_plan_create(const TcPlan *tc, FuPlan **out, std::string *why) {
-    const TcModel &m = tc->m;
+static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
+    if (m.H % 256 != 0 || m.Bp % kTcPairM != 0) {
+        *why = "hidden size must be a multiple of 256 and the padded stream count a multiple of 256 for the tensor-core path";
+        return false;
+    }
     void *fnp = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres) != cudaSuccess || !fnp ||
@@ -605,7 +610,18 @@ static bool fu_plan_create(const TcPlan *tc, FuPlan **out, std::string *why) {
     const size_t H = m.H, Bp = m.Bp, L = m.L, LBH = Bp * H;
     const int mt = m.Bp / kTcPairM, nseg = m.L + 2;
     f->nseg = nseg;
-    bool ok = cudaMalloc((void **) &f->counters, (size_t) nseg * mt * sizeof(unsigned)) == cudaSuccess &&
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&f->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    bool ok = true;
+    for (size_t l = 0; l < L && ok; l++) {
+        ok = cudaMalloc((void **) &f->wih_p[l], 3 * H * H * 2) == cudaSuccess && cudaMalloc((void **) &f->whh_p[l], 3 * H * H * 2) == cudaSuccess;
+        if (!ok) break;
+        pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.wih[l], f->wih_p[l], (int) H, 2, 0, 1);   // n | r | z
+        pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.whh[l], f->whh_p[l], (int) H, 0, 1, 2);   // r | z | n
+    }
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+    ok = ok && cudaMalloc((void **) &f->counters, (size_t) nseg * mt * sizeof(unsigned)) == cudaSuccess &&
               cudaMemset(f->counters, 0, (size_t) nseg * mt * sizeof(unsigned)) == cudaSuccess;
     if (const char *tr = getenv("KOALA_TC_TRACE")) {
         if (tr[0] == '1' && cudaMalloc((void **) &f->trace, 2048 * sizeof(long long)) == cudaSuccess) cudaMemset(f->trace, 0, 2048 * sizeof(long long));
@@ -646,8 +662,8 @@ static bool fu_plan_create(const TcPlan *tc, FuPlan **out, std::string *why) {
                 sg.bias0 = m.bih[l]; sg.bias1 = m.bhh[l]; sg.a1 = m.hb[cur] + l * LBH;
                 put(kMapA0, l == 0 ? m.e : m.hb[nxt] + (l - 1) * LBH, Bp, H, kFuARows);
                 put(kMapA1, m.hb[cur] + l * LBH, Bp, H, kFuARows);
-                put(kMapB0, tc->wih_p[l], 3 * H, H, kGruRows / 2);
-                put(kMapB1, tc->whh_p[l], 3 * H, H, kGruRows / 2);
+                put(kMapB0, f->wih_p[l], 3 * H, H, kGruRows / 2);
+                put(kMapB1, f->whh_p[l], 3 * H, H, kGruRows / 2);
                 put(kMapHp, m.h[cur] + l * LBH, Bp, H, kTcBlockM, true);
                 put(kMapHn, m.h[nxt] + l * LBH, Bp, H, kTcBlockM, true);
                 put(kMapHb, m.hb[nxt] + l * LBH, Bp, H, kTcBlockM, false, true);
@@ -672,7 +688,7 @@ static bool fu_plan_create(const TcPlan *tc, FuPlan **out, std::string *why) {
     }
     {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned) (kFuCluster * tc->num_sms));
+        cfg.gridDim = dim3((unsigned) (kFuCluster * f->num_sms));
         cfg.blockDim = dim3(kFuThreads);
         cfg.dynamicSmemBytes = (size_t) kFuSmemBytes;
         cudaLaunchAttribute attr[1];
@@ -680,7 +696,7 @@ static bool fu_plan_create(const TcPlan *tc, FuPlan **out, std::string *why) {
         attr[0].val.clusterDim.x = kFuCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, tc_fused_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = tc->num_sms / kFuCluster - 4; }
+        if (cudaOccupancyMaxActiveClusters(&n, tc_fused_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = f->num_sms / kFuCluster - 4; }
         if (const char *e = getenv("KOALA_FU_CLUSTERS")) n = std::max(1, std::min(n, atoi(e)));
         f->max_clusters = n;
     }

@@ -1,4 +1,5 @@
-"""Dump the clock64() timeline of one fused mask-estimator launch (KOALA_TC_TRACE=1) -- development aid for the tcgen05 pipeline.
+"""Dump the clock64() timeline of one fused mask-estimator launch -- development aid for the tcgen05 pipeline.
+Needs a trace build of the library:  python -m koala_b200._build -DKOALA_FU_TRACE=1 -otrace.so;  python tools/gpu_trace.py 8192 trace.so
 Per tile of cluster 0 (CTA 0 = pair leader, CTA 1 = its peer): when the producers got it, when its dependency was met, when the
 MMA issuer started / finished, when the accumulator was full and when the epilogue handed the buffer back."""
 import os, sys
