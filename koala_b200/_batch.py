@@ -71,11 +71,12 @@ class BatchKoala(object):
     def _shape(self, shape, time_major: bool = False) -> int:
         if len(shape) == 2:
             shape = (1, shape[0], shape[1]) if time_major else (shape[0], 1, shape[1])
+        want = "[frames][%d][%d]" % (self.num_streams, self.frame_length) if time_major else "[%d][frames][%d]" % (self.num_streams, self.frame_length)
+        if len(shape) != 3:
+            raise KoalaInvalidArgumentError("expected pcm of shape %s, got %s" % (want, tuple(shape)))
         streams, frames = (shape[1], shape[0]) if time_major else (shape[0], shape[1])
-        if len(shape) != 3 or streams != self.num_streams or shape[2] != self.frame_length:
-            raise KoalaInvalidArgumentError(
-                "expected pcm of shape %s, got %s" % ("[frames][%d][%d]" % (self.num_streams, self.frame_length) if time_major else
-                                                      "[%d][frames][%d]" % (self.num_streams, self.frame_length), tuple(shape)))
+        if streams != self.num_streams or shape[2] != self.frame_length:
+            raise KoalaInvalidArgumentError("expected pcm of shape %s, got %s" % (want, tuple(shape)))
         return frames
 
     def process(self, pcm, out=None, time_major: bool = False):

@@ -3,8 +3,10 @@
 // Per-stream state rows (all zero after reset, pv_koala.h:82-90):
 //   tail [Bp][256] int16   previous input frame (analysis overlap)
 //   ola  [Bp][256] fp32    second half of the previous synthesis frame
-//   h    [2][L][Bp][H] fp32  recurrent state, ping-pong by step parity (every unit tile reads all of h(t-1))
-//   hb   [2][L][Bp][H] bf16  the same state rounded to bf16 = GEMM operand of the tensor-core path
+//   h    [L][Bp][H] fp32     recurrent state; bf16 path: updated in place, fp32 path: [2][...] ping-pong by step parity
+//   hb   [2][L][Bp][H] bf16  the same state rounded to bf16 = GEMM operand of the tensor-core path, ping-pong by step parity
+//                            (every unit tile reads all of h(t-1))
+// The bf16 path keeps all of the above in one arena (Engine::create).
 // Scratch per step: feat [Bp][256] (fp32 | bf16), spec [Bp][512] fp32, e [Bp][H], mask [Bp][256] fp32.
 // Bp = B rounded up to 256 (one CTA-pair tile) so that every GEMM tile is full; padding rows stay zero-input and are
 // never copied out.

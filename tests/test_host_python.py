@@ -99,3 +99,17 @@ def test_shard_streams_partitions_exactly():
                     assert spans[r][0] <= s < spans[r][0] + spans[r][1]
     with pytest.raises(ValueError):
         kb.shard_streams(8, 2, 2)
+
+
+def test_batch_layout_validation_without_a_device():
+    """BatchKoala.process accepts [B][T][256] or, time-major, [T][B][256]; the shape check runs before any library call."""
+    from koala_b200._batch import BatchKoala
+    from koala_b200 import KoalaInvalidArgumentError
+    b = object.__new__(BatchKoala)
+    b.num_streams, b.frame_length = 6, 256
+    assert b._shape((6, 10, 256)) == 10 and b._shape((6, 256)) == 1
+    assert b._shape((10, 6, 256), time_major=True) == 10 and b._shape((6, 256), time_major=True) == 1
+    for shape, tm in (((10, 6, 256), False), ((6, 10, 256), True), ((6, 10, 255), False), ((6,), False)):
+        with pytest.raises(KoalaInvalidArgumentError):
+            b._shape(shape, time_major=tm)
+    b._handle = None      # nothing to release
