@@ -24,3 +24,10 @@ for cta in range(2):
         if t[b+4] == 0 and t[b+0] == 0: continue
         kbs = [r(x) for x in t[b+32:b+48] if x]
         print(f" tile {it:2d}: prod got {r(t[b+0])} dep ok {r(t[b+12])} last load {r(t[b+1])} | mma start {r(t[b+2])} done {r(t[b+3])} ({len(kbs)} kb, {(kbs[-1]-kbs[0])//max(len(kbs)-1,1) if kbs else 0}/kb) | epi ready {r(t[b+4])} acc_full {r(t[b+5])} handback {r(t[b+6])} | stores {r(t[b+9])} {r(t[b+11])}")
+if len(sys.argv) > 3:       # per-k-block detail of one tile of CTA 0: when the A producers saw the slot free, when the MMA issuer saw it full
+    it = int(sys.argv[3]); t = tr[0]; t0 = t[1020]; b = it * 48
+    free = [int(x - t0) for x in t[b+16:b+32]]; full = [int(x - t0) for x in t[b+32:b+48]]
+    print(f"tile {it}: slot free (producer)  ", free)
+    print(f"tile {it}: data full (MMA issuer)", full)
+    print("   full - free (load latency)      ", [f - e for f, e in zip(full, free)])
+    print("   d(full) per k-block             ", [full[i + 1] - full[i] for i in range(15)])

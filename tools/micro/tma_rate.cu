@@ -103,5 +103,13 @@ int main() {
         run<128, 3, 4>(fn, base, rows, kcols, grid);
         run<64, 6, 4>(fn, base, rows, kcols, grid);
     }
+    // the same 16 MB as a K-blocked matrix: row pitch 128 B, so a [128 x 64] box is one contiguous 16 KB range
+    printf("row pitch 128 B (contiguous boxes):\n");
+    for (int grid : {1, 148}) {
+        run<128, 4>(fn, base, rows * (kcols / 64), 64, grid);
+        run<128, 4, 2>(fn, base, rows * (kcols / 64), 64, grid);
+        run<128, 3, 4>(fn, base, rows * (kcols / 64), 64, grid);
+        run<96, 4, 4>(fn, base, rows * (kcols / 64), 64, grid);
+    }
     return 0;
 }
