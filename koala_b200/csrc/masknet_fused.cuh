@@ -707,9 +707,11 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
 // one mask-estimator step = one launch: hb[cur] / h[cur] hold state t-1, results go to hb[cur ^ 1] / h[cur ^ 1]
 static int fu_masknet_step(FuPlan *f, int cur, cudaStream_t st) {
     FuArgs &a = f->args[cur];
-    a.epoch = ++f->epoch;
+    a.epoch = f->epoch + 1;
     const int clusters = a.total_tiles < f->max_clusters ? a.total_tiles : f->max_clusters;
-    launch_pdl(true, tc_fused_kernel, dim3((unsigned) (kFuCluster * clusters)), dim3(kFuThreads), (size_t) kFuSmemBytes, st, a);
+    // the epoch only advances with a launch that was accepted: the counters then stand at epoch * (increments per step), which
+    // is what the next launch waits for (the caller reports the launch error through cudaGetLastError)
+    if (launch_pdl(true, tc_fused_kernel, dim3((unsigned) (kFuCluster * clusters)), dim3(kFuThreads), (size_t) kFuSmemBytes, st, a) == cudaSuccess) f->epoch = a.epoch;
     return 1;
 }
 
