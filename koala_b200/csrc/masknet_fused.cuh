@@ -22,7 +22,8 @@
 //   GRU epilogue: two PASSES of 32 units through two staging buffers; the state warp TMA-stores a finished pass (fp32 h(t)
 //   in place of h(t-1), plus its bf16 copy) and requests the fp32 h(t-1) box of the pass two ahead into the drained buffer.
 //   Linear epilogue: the accumulator is handed back after four TMEM loads; outputs are staged in a separate 32 KB region
-//   (encoder: the CTA's whole [128][128] bf16 tile, decoder: two rounds of [128][64] fp32) and TMA-stored by warp 22.
+//   (encoder: the CTA's whole [128][128] bf16 tile; decoder: [128][128] fp32, half of it in the by then idle GRU boxes) and
+//   TMA-stored by warp 22.
 // Shared memory: 5 operand stages x 28 KB + 48 KB GRU staging + 32 KB linear staging + barriers / biases = 223 KB.
 //
 // What bounds it (8192 streams, B200; profiles/r01_step_summary.md): operand delivery.  Skipping every tcgen05.mma leaves
@@ -123,7 +124,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
     uint64_t *box_ready = bars + 2 * kStages + 4;        // [2]: staging buffer is free (linear) / holds h(t-1) (GRU)
     uint64_t *staged = bars + 2 * kStages + 6;           // [2]: the epilogue has staged a pass in the buffer
     uint64_t *lin_free = bars + 2 * kStages + 8, *lin_staged = bars + 2 * kStages + 9;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 10);
+    uint64_t *gru_done = bars + 2 * kStages + 10;         // the state warp has drained: the GRU staging boxes are free for good
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 11);
     float *s_bias = reinterpret_cast<float *>(tail + 256);   // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,6 +159,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 mbar_init(&staged[b], kFuArrivals);
             }
             mbar_init(lin_free, 1);
+            mbar_init(gru_done, 1);
             mbar_init(lin_staged, kFuArrivals);
             fence_mbar_init();
         }
@@ -371,15 +374,17 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 advance(cur);
                 ++pc;
             }
-            bulk_wait_all();                                 // shared memory must outlive the last stores
+            bulk_wait_read();                                // shared memory must outlive the last stores' reads (kernel completion covers the writes)
+            mbar_arrive(gru_done);                           // ... and from here on the decoder tiles may stage in the GRU boxes
         }
         __syncwarp();
     } else if (warp == kFuLinWarp) {
         // ===================================================== linear-tile store warp: encoder / decoder outputs leave through
-        // their own 32 KB staging region in ROUNDS (encoder: the whole [128][128] bf16 tile of this CTA, decoder: two halves
-        // of [128][64] fp32), so they never compete with the GRU passes for staging buffers.  Per round: wait until the
-        // epilogue warps have staged it, TMA-store its two boxes, free the region once they have been read; after an encoder
-        // tile, wait for the stores to complete and release the dependent GRU tiles.
+        // their own 32 KB staging region, so they never compete with the GRU passes for staging buffers: the encoder's whole
+        // [128][128] bf16 tile of this CTA fits; the decoder's [128][128] fp32 tile takes the two fp32 GRU boxes as well, which
+        // are idle by then (a pair's decoder tiles come after all its GRU tiles; `gru_done`).  Per tile: wait until the epilogue
+        // warps have staged it, TMA-store its boxes, free the region once they have been read; after an encoder tile, wait
+        // for the stores to complete and release the dependent GRU tiles.
         pdl_wait();
         if (elect_one()) {
             const int row0 = (int) rank * kTcBlockM;
@@ -390,27 +395,27 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 if (sg.mode == kTcGru) continue;
                 const CUtensorMap *map = args.maps + t.s * kFuMapsPerSeg + kMapHn;
                 const int row = t.m * kTcPairM + row0, col = (t.n0 + qn) * kFuLinN;
-                const int rounds = sg.mode == kTcEnc ? 1 : 2;
-                for (int h = 0; h < rounds; ++h, ++lc) {
-                    mbar_wait(lin_staged, lc & 1);
-                    if (sg.mode == kTcEnc) {       // boxes of 64 bf16 columns
-                        tma_store_2d(map, s_lin, col, row);
-                        tma_store_2d(map, s_lin + kFuBoxF32, col + 64, row);
-                    } else {                       // boxes of 32 fp32 columns
-                        tma_store_2d(map, s_lin, col + 64 * h, row);
-                        tma_store_2d(map, s_lin + kFuBoxF32, col + 64 * h + 32, row);
-                    }
-                    bulk_commit();
-                    bulk_wait_read();
-                    mbar_arrive(lin_free);
+                mbar_wait(lin_staged, lc & 1);
+                if (sg.mode == kTcEnc) {           // two boxes of 64 bf16 columns
+                    tma_store_2d(map, s_lin, col, row);
+                    tma_store_2d(map, s_lin + kFuBoxF32, col + 64, row);
+                } else {                           // four boxes of 32 fp32 columns: two in the linear region, two in the GRU boxes
+                    tma_store_2d(map, s_lin, col, row);
+                    tma_store_2d(map, s_lin + kFuBoxF32, col + 32, row);
+                    tma_store_2d(map, s_f32, col + 64, row);
+                    tma_store_2d(map, s_f32 + kFuBoxF32, col + 96, row);
                 }
+                bulk_commit();
+                bulk_wait_read();
+                mbar_arrive(lin_free);
+                ++lc;
                 if (sg.done >= 0) {
                     bulk_wait_all();                         // this tile's rows are in global memory
                     fence_proxy_async_all();
                     red_release_gpu(args.counters + (size_t) sg.done * args.num_m_tiles + t.m, 1u);
                 }
             }
-            bulk_wait_all();
+            bulk_wait_read();                                // every store has read its staging box; the grid's completion orders the writes
         }
         __syncwarp();
     } else if (warp >= 5 && warp < kTcStateWarp) {
@@ -466,9 +471,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (mode != kTcGru) {
                 // linear tile: my warp owns 32 of the 128 outputs (columns part * 32 ..), one row per thread.  The accumulator
-                // buffer is handed back after four TMEM loads; the outputs are staged in the linear staging region (128B-
-                // swizzled boxes) and stored by the linear store warp: the encoder's tile in one round, the decoder's fp32
-                // tile in two rounds of 64 columns (warps with part / 2 == round write).
+                // buffer is handed back after four TMEM loads; the outputs are staged in 128B-swizzled boxes (the linear
+                // staging region, plus the idle GRU boxes for the decoder's fp32 tile) and stored by the linear store warp.
                 float acc[32];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tmem_ld8(t0 + part * 32 + 8 * j, *reinterpret_cast<float(*)[8]>(acc + 8 * j));
@@ -486,24 +490,23 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                     const float v = acc[i] + sb[part * 32 + i];
                     acc[i] = mode == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
                 }
-                const int rounds = mode == kTcEnc ? 1 : 2;
-                for (int h = 0; h < rounds; ++h, ++lc) {
-                    mbar_wait(lin_free, (lc & 1) ^ 1);       // the previous round's stores have read the region
-                    if (mode == kTcEnc) {                    // box part / 2 holds columns 64 (part / 2) ..; my 32 columns = 4 chunks of 8 bf16
-                        uint8_t *rowp = s_lin + (part >> 1) * kFuBoxF32 + row_in_cta * 128;
+                mbar_wait(lin_free, (lc & 1) ^ 1);           // the previous linear tile's stores have read the staging boxes
+                if (mode == kTcEnc) {                        // box part / 2 holds columns 64 (part / 2) ..; my 32 columns = 4 chunks of 8 bf16
+                    uint8_t *rowp = s_lin + (part >> 1) * kFuBoxF32 + row_in_cta * 128;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + j) ^ sw) << 4)) = pack_bf16x8(acc + 8 * j);
-                    } else if ((part >> 1) == h) {           // box part & 1 holds my 32 fp32 columns = 8 chunks of 4
-                        uint8_t *rowp = s_lin + (part & 1) * kFuBoxF32 + row_in_cta * 128;
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + j) ^ sw) << 4)) = pack_bf16x8(acc + 8 * j);
+                } else {                                     // my 32 fp32 columns = one box of 8 chunks of 4: parts 0,1 in the linear region, 2,3 in the GRU boxes
+                    if (part >= 2) mbar_wait(gru_done, 0);
+                    uint8_t *rowp = (part < 2 ? s_lin : s_f32) + (part & 1) * kFuBoxF32 + row_in_cta * 128;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4 *>(rowp + ((j ^ sw) << 4)) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(lin_staged);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4 *>(rowp + ((j ^ sw) << 4)) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(lin_staged);
+                ++lc;
                 continue;
             }
             // GRU tile: two passes of 32 units through the staging buffers
