@@ -97,6 +97,30 @@ def test_state_carry_reset_and_subset_reset(library_path, random_model_path, pre
     eng.delete()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("hidden,layers", [(256, 1), (768, 3)])
+def test_other_model_shapes(library_path, tmp_path, hidden, layers, precision):
+    """The model file fixes the hidden size (a multiple of 256 on the tensor-core path) and the number of GRU layers; the fused
+    kernel's tile list (L + 2 segments, H / 64 unit tiles, H / 64 k-blocks per part) must follow it.  300 streams = two
+    256-stream tiles, so the per-tile dependency counters of both tiles are exercised."""
+    from koala_b200 import spec
+    path = str(tmp_path / f"model_{hidden}_{layers}.kpv")
+    spec.save_model(path, spec.random_model(seed=hidden + layers, hidden=hidden, layers=layers), hidden=hidden, layers=layers)
+    n, frames = 300, 6
+    pcm = synth_pcm(n, frames, seed=hidden)
+    eng = kb.BatchKoala(n, model_path=path, precision=precision)
+    out = eng.process(pcm)
+    ob, ref = run_oracle(path, precision, pcm)
+    diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= LSB_TOL, (diff.max(), np.argwhere(diff > LSB_TOL)[:5])
+    mask = eng.debug_read("mask", (n, 256), np.float32)
+    np.testing.assert_allclose(mask, np.stack([ob.stream(s).last_mask for s in range(n)]), rtol=MASK_RTOL, atol=1e-6)
+    for l in range(layers):
+        h = eng.debug_read(f"h{l}", (n, hidden), np.float32)
+        np.testing.assert_allclose(h, np.stack([ob.stream(s).h[l] for s in range(n)]), atol=2e-4)
+    eng.delete()
+
+
 def test_long_host_call_layouts_agree(library_path, random_model_path):
     """A 140-frame host call exercises the ingest pipeline's output blocks (32-frame blocks, a short last block, a 4-frame last
     chunk); the time-major entry point (host and device buffers) and frame-by-frame calls must give the same samples."""
