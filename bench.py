@@ -43,8 +43,8 @@ BYTES_PER_FRAME = 1024 + 2 * STATE_BYTES                                        
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
-# of this workload (fused kernel, profiles/r01c_step_ncu_full_selected_metrics.csv); other workloads have no capture -> null
-NCU_DRAM_TRAFFIC_BYTES = {"cfg4_8192_per_gpu_bf16": 61.4e6 + 15.9e6}
+# of this workload (fused kernel, profiles/r01d_step_ncu_full_selected_metrics.csv); other workloads have no capture -> null
+NCU_DRAM_TRAFFIC_BYTES = {"cfg4_8192_per_gpu_bf16": 61.4e6 + 16.9e6}
 
 
 def synth_pcm(n_streams: int, n_frames: int, seed: int) -> np.ndarray:
