@@ -335,8 +335,8 @@ def main():
                 peaks = json.load(f)
         except OSError:
             pass
-        fused = prof.get("masknet", (0.0, 0))[1] > 0            # bf16 path: encoder -> GRU layers -> decoder in ONE kernel
-        gru_ms, gru_n = prof["masknet"] if fused else prof["gru"]
+        fused = precision == "bf16"                            # bf16 path: encoder -> GRU layers -> decoder in ONE kernel
+        gru_ms, gru_n = prof["masknet"] if fused else prof["gru"]   # fp32 path: the GRU layer kernel dominates
         dom_flops = (FLOPS_PER_FRAME if fused else GRU_FLOPS_PER_STREAM) * streams
         step_prof_ms = sum(v[0] for v in prof.values()) / max(prof_steps, 1)
         shares = {k: (v[0] / max(sum(x[0] for x in prof.values()), 1e-12)) for k, v in prof.items()}
@@ -344,8 +344,7 @@ def main():
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
             achieved = dom_flops / (gru_ms / max(gru_n, 1) * 1e-3) / 1e12 if gru_n else None
-            roofline = {"bound": "tensor", "kernel": "tc_fused_kernel (encoder + GRU layers + decoder GEMMs of one step, all streams)" if fused
-                        else "tc_masknet_kernel<GRU> (one GRU layer, all streams)", "achieved": achieved,
+            roofline = {"bound": "tensor", "kernel": "tc_fused_kernel (encoder + GRU layers + decoder GEMMs of one step, all streams)", "achieved": achieved,
                         "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                         "traffic": NCU_DRAM_TRAFFIC_BYTES.get(args.workload) if not args.streams else None,
                         "peak_source": peak_src, "avg_launch_ms": gru_ms / max(gru_n, 1),

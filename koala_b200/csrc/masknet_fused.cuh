@@ -580,7 +580,7 @@ struct FuPlan {
     unsigned *counters = nullptr;
     CUtensorMap *d_maps[2] = {};      // [parity][nseg][kFuMapsPerSeg]
     FuArgs args[2];                   // by parity of the buffer that holds h(t-1)
-    long long *trace = nullptr;       // 2 x 1024 clock64 slots of CTAs 0 and 1 (KOALA_TC_TRACE=1), else nullptr
+    long long *trace = nullptr;       // 2 x 1024 clock64 slots of CTAs 0 and 1 (allocated when KOALA_FU_TRACE_BUF=1; written by -DKOALA_FU_TRACE=1 builds), else nullptr
 };
 
 static void fu_plan_destroy(FuPlan *f) {
@@ -626,7 +626,7 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     ok = ok && cudaMalloc((void **) &f->counters, (size_t) nseg * mt * sizeof(unsigned)) == cudaSuccess &&
               cudaMemset(f->counters, 0, (size_t) nseg * mt * sizeof(unsigned)) == cudaSuccess;
-    if (const char *tr = getenv("KOALA_TC_TRACE")) {
+    if (const char *tr = getenv("KOALA_FU_TRACE_BUF")) {
         if (tr[0] == '1' && cudaMalloc((void **) &f->trace, 2048 * sizeof(long long)) == cudaSuccess) cudaMemset(f->trace, 0, 2048 * sizeof(long long));
     }
     for (int cur = 0; cur < 2 && ok; cur++) {

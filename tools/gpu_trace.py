@@ -4,7 +4,7 @@ Per tile of cluster 0 (CTA 0 = pair leader, CTA 1 = its peer): when the producer
 MMA issuer started / finished, when the accumulator was full and when the epilogue handed the buffer back."""
 import os, sys
 import numpy as np
-os.environ["KOALA_TC_TRACE"] = "1"
+os.environ["KOALA_FU_TRACE_BUF"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import koala_b200 as kb
 from koala_b200 import spec
