@@ -14,4 +14,5 @@ echo "== reference arm"; timeout 300 python bench.py --impl reference --steps 5 
 CMD="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 8"
 echo "== ncu launches"; timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 9 -c 30 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "== ncu full";     timeout 600 ncu --set full --clock-control none --import-source on -s 9 -c 3 -f -o gpurun_out/step_${TAG} $CMD > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log | cut -c1-120
-echo "== trace"; timeout 100 python tools/gpu_trace.py 8192 gpurun_lib_TRACE.so 2>&1 | head -14 > gpurun_out/trace_${TAG}.txt; head -3 gpurun_out/trace_${TAG}.txt
+echo "== trace"; [ -f gpurun_lib_TRACE.so ] || python -m koala_b200._build -DKOALA_FU_TRACE=1 -ogpurun_lib_TRACE.so > /dev/null 2>&1
+timeout 100 python tools/gpu_trace.py 8192 gpurun_lib_TRACE.so 2>&1 | head -14 > gpurun_out/trace_${TAG}.txt; head -3 gpurun_out/trace_${TAG}.txt
