@@ -334,7 +334,7 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
             if (prof) prof->begin(kKernFrontend, st);
             launch_pdl(false, frontend_kernel<float>, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->tail, p->spec, feat, p->tables);
             if (prof) { prof->end(st); prof->begin(kKernEnc, st); }
-            launch_pdl(false, linear_fp32_kernel<kActRelu>, dim3(Bp / kF32Bm, H / 64), dim3(256), 0, st, feat, p->enc_w, p->enc_b, e, kBins, H);
+            launch_pdl(false, linear_fp32_kernel<kActRelu>, dim3(Bp / kF32Bm, H / kF32LinN), dim3(256), 0, st, feat, p->enc_w, p->enc_b, e, kBins, H);
             if (prof) prof->end(st);
             const float *x = e;
             for (int l = 0; l < L; l++) {
@@ -345,7 +345,7 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
                 x = p->h[nxt] + l * LBH;
             }
             if (prof) prof->begin(kKernDec, st);
-            launch_pdl(false, linear_fp32_kernel<kActSigmoid>, dim3(Bp / kF32Bm, kBins / 64), dim3(256), 0, st, x, p->dec_w, p->dec_b, p->mask, H, kBins);
+            launch_pdl(false, linear_fp32_kernel<kActSigmoid>, dim3(Bp / kF32Bm, kBins / kF32LinN), dim3(256), 0, st, x, p->dec_w, p->dec_b, p->mask, H, kBins);
             if (prof) prof->end(st);
             launches_ += 3 + L;
         } else {

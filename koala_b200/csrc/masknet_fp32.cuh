@@ -69,53 +69,51 @@ __device__ __forceinline__ void stash_w(float (*Ws)[LD], const WTile &r, int tid
     }
 }
 
-// out[m][n] = act(bias[n] + sum_k A[m][k] W[n][k]);  grid = (M/64, N/64), block = 256 (tx = 16 columns x 4, ty = 16 x 4 rows)
+// out[m][n] = act(bias[n] + sum_k A[m][k] W[n][k]);  grid = (M/64, N/16), block = 256 (tx = column, ty = 16 x 4 rows).
+// The tile is only 16 outputs wide (the GRU kernel's shape): at 256 streams a 64-wide tile left the decoder with 16 CTAs.
+constexpr int kF32LinN = 16;
 template <int ACT>
 __global__ void __launch_bounds__(256)
 linear_fp32_kernel(const float *__restrict__ A, const __nv_bfloat16 *__restrict__ W, const float *__restrict__ bias,
                    float *__restrict__ out, int K, int N) {
     __shared__ __align__(16) float As[kF32Bk][kF32Bm + kF32Pad];
-    __shared__ __align__(16) float Ws[kF32Bk][64 + kF32Pad];
+    __shared__ __align__(16) float Ws[kF32Bk][kF32LinN + kF32Pad];
     pdl_launch_dependents();
     pdl_wait();
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.x * kF32Bm, n0 = blockIdx.y * 64;
+    const int m0 = blockIdx.x * kF32Bm, n0 = blockIdx.y * kF32LinN;
     auto w_row = [&](int row) { return W + (size_t) (n0 + row) * K; };
-    float acc[4][4] = {};
+    float acc[4] = {};
     ATile ra;
     WTile rw;
     fetch_a(ra, A, K, m0, 0, tid);
-    fetch_w<64>(rw, w_row, 0, tid);
+    fetch_w<kF32LinN>(rw, w_row, 0, tid);
     for (int k0 = 0; k0 < K; k0 += kF32Bk) {
         stash_a(As, ra, tid);
-        stash_w<64, 64 + kF32Pad>(Ws, rw, tid);
+        stash_w<kF32LinN, kF32LinN + kF32Pad>(Ws, rw, tid);
         __syncthreads();
         if (k0 + kF32Bk < K) {       // next tile's loads fly while this tile is multiplied
             fetch_a(ra, A, K, m0, k0 + kF32Bk, tid);
-            fetch_w<64>(rw, w_row, k0 + kF32Bk, tid);
+            fetch_w<kF32LinN>(rw, w_row, k0 + kF32Bk, tid);
         }
 #pragma unroll 16
         for (int kk = 0; kk < kF32Bk; ++kk) {
             const float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w};
-            float wv[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) wv[c] = Ws[kk][tx + 16 * c];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+            const float w = Ws[kk][tx];
+            acc[0] = fmaf(a.x, w, acc[0]);
+            acc[1] = fmaf(a.y, w, acc[1]);
+            acc[2] = fmaf(a.z, w, acc[2]);
+            acc[3] = fmaf(a.w, w, acc[3]);
         }
         __syncthreads();
     }
+    const int n = n0 + tx;
+    const float bn = bias[n];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int m = m0 + ty * 4 + r, n = n0 + tx + 16 * c;
-            const float v = acc[r][c] + bias[n];
-            out[(size_t) m * N + n] = ACT == kActRelu ? fmaxf(v, 0.0f) : sigmoid_f(v);
-        }
+    for (int r = 0; r < 4; ++r) {
+        const float v = acc[r] + bn;
+        out[(size_t) (m0 + ty * 4 + r) * N + n] = ACT == kActRelu ? fmaxf(v, 0.0f) : sigmoid_f(v);
+    }
 }
 
 // One GRU layer step for a tile of 64 streams x 16 hidden units (PyTorch gate order r | z | n):
