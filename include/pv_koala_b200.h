@@ -102,7 +102,13 @@ PV_API pv_status_t pv_koala_batch_process_time_major(pv_koala_batch_t *object, c
 
 /* Device buffers only, enqueue-only: frame t of stream s at base + s * stream_stride + t * 256 samples (16-byte aligned,
  * stride % 8 == 0).  cuda_stream: a cudaStream_t passed as void* and taken literally (NULL = CUDA's legacy default stream).
- * Work is ordered on that stream like any other kernel; pv_koala_batch_synchronize waits for the whole device. */
+ * Work is ordered on that stream like any other kernel; pv_koala_batch_synchronize waits for the whole device.
+ * A handle's steps mutate its per-stream state, so the library orders them itself when the stream changes between calls (or
+ * between this call and pv_koala_batch_reset / a host-buffer call): the new stream waits for what was enqueued on the previous
+ * one.  Handles are not thread-safe: serialise the calls on one handle (as the reference's bindings do for pv_koala_t).
+ * Several handles on one device may be used concurrently from one process; the library serialises their mask-estimator launches
+ * on the device.  Sharing the device with OTHER processes through MPS while a "bf16" handle is stepping is not supported (the
+ * mask-estimator kernel needs its whole grid resident). */
 PV_API pv_status_t pv_koala_batch_process_async(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,
                                                 int32_t num_frames, int64_t stream_stride, void *cuda_stream);
 PV_API pv_status_t pv_koala_batch_synchronize(pv_koala_batch_t *object);
@@ -110,12 +116,16 @@ PV_API pv_status_t pv_koala_batch_synchronize(pv_koala_batch_t *object);
 /* stream_ids == NULL resets every stream (pv_koala_reset semantics per stream). */
 PV_API pv_status_t pv_koala_batch_reset(pv_koala_batch_t *object, const int32_t *stream_ids, int32_t num_ids);
 PV_API pv_status_t pv_koala_batch_num_streams(const pv_koala_batch_t *object, int32_t *num_streams);
+/* CUDA ordinal of the device the handle's streams live on (what "best" / "gpu" / "gpu:K" resolved to) */
+PV_API pv_status_t pv_koala_batch_device(const pv_koala_batch_t *object, int32_t *device_index);
 PV_API pv_status_t pv_koala_batch_delay_sample(const pv_koala_batch_t *object, int32_t *delay_sample);
 /* kernels launched so far by this handle (bench.py's gpu_launches) */
 PV_API pv_status_t pv_koala_batch_kernel_launches(const pv_koala_batch_t *object, int64_t *launches);
-/* Per-kernel-class CUDA-event timing on the launching stream (classes: 0 analysis/STFT, 1 encoder GEMM, 2 GRU layer,
- * 3 decoder GEMM, 4 synthesis/iSTFT).  Enable, run steps, then read: read synchronises, returns summed milliseconds and
- * launch counts per class since the previous read.  Off by default (events perturb back-to-back launches). */
+/* Per-kernel-class CUDA-event timing on the launching stream.  SIX classes: 0 analysis/STFT, 1 encoder GEMM, 2 GRU layer,
+ * 3 decoder GEMM, 4 synthesis/iSTFT (1-3: "fp32" handles), 5 fused mask estimator (encoder + GRU layers + decoder in one kernel,
+ * "bf16" handles).  Enable, run steps, then read: read synchronises and returns summed milliseconds and launch counts per class
+ * since the previous read; num_classes must be >= 6 (INVALID_ARGUMENT otherwise; INVALID_STATE if profiling is off).
+ * Off by default (events perturb back-to-back launches). */
 PV_API pv_status_t pv_koala_batch_profile(pv_koala_batch_t *object, int32_t enable);
 PV_API pv_status_t pv_koala_batch_profile_read(pv_koala_batch_t *object, double *ms_per_class, int64_t *launches_per_class,
                                                int32_t num_classes);

@@ -53,6 +53,11 @@ class BatchKoala(object):
                                                    precision.encode(), byref(self._handle)), 'Initialization failed')
         self.num_streams = int(num_streams)
         self.precision = precision
+        dev = c_int32(-1)
+        library.pv_koala_batch_device.argtypes = [H, POINTER(c_int32)]
+        library.pv_koala_batch_device.restype = c_int
+        check(library, library.pv_koala_batch_device(self._handle, byref(dev)), 'device query failed')
+        self.device_index = dev.value                 # CUDA ordinal the handle's streams live on
         self.frame_length = library.pv_koala_frame_length()
         self.sample_rate = library.pv_sample_rate()
         self.delay_sample = 256
@@ -89,6 +94,9 @@ class BatchKoala(object):
             pcm = np.ascontiguousarray(pcm, dtype=np.int16)
             if out is None:
                 out = np.empty_like(pcm)
+            elif not (isinstance(out, np.ndarray) and out.dtype == np.int16 and out.shape == pcm.shape and out.flags.c_contiguous
+                      and out.flags.writeable):
+                raise KoalaInvalidArgumentError("out must be a writeable C-contiguous int16 numpy array of pcm's shape")
             check(self._library, entry(self._handle, pcm.ctypes.data, out.ctypes.data, frames), 'Processing failed')
             return out
         import torch  # device tensors (or pinned host tensors) only
@@ -97,6 +105,11 @@ class BatchKoala(object):
         frames = self._shape(tuple(pcm.shape), time_major)
         if out is None:
             out = torch.empty_like(pcm)
+        elif not (isinstance(out, torch.Tensor) and out.dtype == torch.int16 and out.shape == pcm.shape and out.is_contiguous()
+                  and out.device == pcm.device):
+            raise KoalaInvalidArgumentError("out must be a contiguous int16 torch tensor of pcm's shape on pcm's device")
+        if pcm.is_cuda and pcm.device.index != self.device_index:
+            raise KoalaInvalidArgumentError("pcm lives on cuda:%d but this engine runs on cuda:%d" % (pcm.device.index, self.device_index))
         if pcm.is_cuda and not time_major:
             stream = torch.cuda.current_stream(pcm.device).cuda_stream
             check(self._library, self._library.pv_koala_batch_process_async(

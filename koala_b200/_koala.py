@@ -12,26 +12,20 @@ from typing import Sequence
 
 
 class KoalaError(Exception):
+    """Base class of every engine error.  Besides the summary line it carries the engine's message stack
+    (pv_get_error_stack), innermost message first, as the reference binding's exception does (same attribute names)."""
+
     def __init__(self, message: str = '', message_stack: Sequence[str] = None):
         super().__init__(message)
         self._message = message
-        self._message_stack = list() if message_stack is None else message_stack
+        self._message_stack = tuple(message_stack or ())
+
+    message = property(lambda self: self._message)
+    message_stack = property(lambda self: self._message_stack)
 
     def __str__(self):
-        message = self._message
-        if len(self._message_stack) > 0:
-            message += ':'
-            for i, line in enumerate(self._message_stack):
-                message += '\n  [%d] %s' % (i, line)
-        return message
-
-    @property
-    def message(self) -> str:
-        return self._message
-
-    @property
-    def message_stack(self) -> Sequence[str]:
-        return self._message_stack
+        head = self._message + (':' if self._message_stack else '')
+        return '\n'.join([head] + ['  [%d] %s' % entry for entry in enumerate(self._message_stack)])
 
 
 class KoalaMemoryError(KoalaError):

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "koala_common.cuh"
 #include "masknet_fp32.cuh"
@@ -136,7 +137,60 @@ struct Engine::Impl {
     size_t arena_bytes = 0;
     KernelProfiler *prof = nullptr;
     std::vector<void *> allocs;
+    // Ordering of state-mutating work across streams: every step reads and writes the per-stream state rows (and the fused
+    // kernel's dependency counters), so work enqueued on a new stream must run after what was enqueued on the previous one.
+    // The event is recorded lazily, on the PREVIOUS stream at the moment the stream changes (an event record between two
+    // kernels of the same stream would break their programmatic-dependent-launch overlap).
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
+    cudaEvent_t ev_order = nullptr;
 };
+
+// Makes `st` wait for everything enqueued so far on `prev` (falls back to a device synchronisation if `prev` is no longer a
+// valid stream, e.g. a caller's stream that has since been destroyed).
+static cudaError_t chain_streams(cudaStream_t prev, cudaStream_t st, cudaEvent_t *ev) {
+    if (prev == st) return cudaSuccess;
+    if (!*ev) {
+        cudaError_t e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    if (cudaEventRecord(*ev, prev) != cudaSuccess) {
+        cudaGetLastError();
+        return cudaDeviceSynchronize();
+    }
+    return cudaStreamWaitEvent(st, *ev, 0);
+}
+
+// The fused mask-estimator kernel spins on dependency counters and relies on its whole grid being co-resident
+// (masknet_fused.cuh).  Two such grids from different engines (every pv_koala_t / pv_koala_batch_t owns one) running
+// concurrently on one device could each hold part of the SMs and wait for clusters that cannot be scheduled.  Fused launches
+// of different engines of this process are therefore serialised per device: an engine that launches after another one makes its
+// stream wait for the other engine's stream first.  One engine on one stream (the steady state) never pays for this.
+// (Other PROCESSES sharing the device through MPS are outside what a library can order; see include/pv_koala_b200.h.)
+namespace {
+struct FusedOwner {
+    const void *impl = nullptr;
+    cudaStream_t stream = nullptr;
+};
+std::mutex g_fused_mu;
+FusedOwner g_fused_last[64];
+}  // namespace
+
+static cudaError_t serialize_fused_launches(int device, const void *impl, cudaStream_t st, cudaEvent_t *ev) {
+    if (device < 0 || device >= 64) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(g_fused_mu);
+    FusedOwner &o = g_fused_last[device];
+    cudaError_t e = cudaSuccess;
+    if (o.impl && o.impl != impl) e = chain_streams(o.stream, st, ev);
+    o.impl = impl;
+    o.stream = st;
+    return e;
+}
+static void forget_fused_owner(int device, const void *impl) {
+    if (device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lock(g_fused_mu);
+    if (g_fused_last[device].impl == impl) g_fused_last[device] = FusedOwner();
+}
 
 #define KCHECK(expr)                                                                                      \
     do {                                                                                                  \
@@ -170,8 +224,6 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
         return kInvalidArgument;
     }
     KCHECK(cudaSetDevice(device));
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);   // the whole L2 for the normal policy (see the state arena below)
-    cudaGetLastError();
     cudaDeviceProp prop;
     KCHECK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -287,7 +339,11 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
 Engine::~Engine() {
     if (!p_) return;
     cudaSetDevice(device_);
+    if (p_->has_last && p_->last_stream != p_->stream) cudaDeviceSynchronize();   // work may still be queued on a caller's stream
+    cudaGetLastError();
     if (p_->stream) cudaStreamSynchronize(p_->stream);
+    forget_fused_owner(device_, p_);
+    if (p_->ev_order) cudaEventDestroy(p_->ev_order);
     if (p_->fu) fu_plan_destroy(p_->fu);
     delete p_->prof;
     for (void *a : p_->allocs) cudaFree(a);
@@ -317,6 +373,11 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
     cudaStream_t st = (cudaStream_t) stream_;
+    if (frames == 0) return kSuccess;
+    if (p->has_last) KCHECK(chain_streams(p->last_stream, st, &p->ev_order));
+    p->last_stream = st;
+    p->has_last = true;
+    if (p->fu) KCHECK(serialize_fused_launches(device_, p, st, &p->ev_order));
     const int B = n_, Bp = npad_, H = p->H, L = p->L;
     const size_t LBH = (size_t) Bp * H;
     // STFT kernels: warps walk a fixed number of streams each; with B / resident warps rounded DOWN the grid is slightly larger
@@ -492,6 +553,10 @@ Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> 
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
     const size_t Bp = npad_, H = p->H, L = p->L;
+    // the state rows may still be in use by steps enqueued on a caller's stream (process_device): run after them
+    if (p->has_last) KCHECK(chain_streams(p->last_stream, p->stream, &p->ev_order));
+    p->last_stream = p->stream;
+    p->has_last = true;
     if (!stream_ids) {
         KCHECK(cudaMemsetAsync(p->tail, 0, Bp * kFrame * sizeof(int16_t), p->stream));
         KCHECK(cudaMemsetAsync(p->ola, 0, Bp * kFrame * sizeof(float), p->stream));
@@ -534,7 +599,11 @@ void Engine::set_profile(bool on) {
 }
 
 Status Engine::profile_read(double *ms, long long *count, int n_classes, std::vector<std::string> *errors) {
-    if (!p_->prof || n_classes < kKernClasses) {
+    if (n_classes < kKernClasses) {
+        if (errors) errors->push_back("`num_classes` must be at least 6 (analysis, encoder, GRU, decoder, synthesis, fused mask estimator).");
+        return kInvalidArgument;
+    }
+    if (!p_->prof) {
         if (errors) errors->push_back("Profiling is not enabled.");
         return kInvalidState;
     }

@@ -70,8 +70,11 @@ bool parse_device(const char *s, bool *is_cpu, int *index) {
     if (!*d) return false;
     for (const char *q = d; *q; ++q)
         if (*q < '0' || *q > '9') return false;
+    char *end = nullptr;
+    const long v = strtol(d, &end, 10);
+    if (*end || v < 0 || v > 4096) return false;   // digits only (checked above), bounded: no int overflow
     *is_cpu = c;
-    *index = atoi(d);
+    *index = (int) v;
     return true;
 }
 
@@ -348,6 +351,7 @@ static pv_status_t batch_process(pv_koala_batch_t *object, const int16_t *pcm, i
     if (!pcm) return fail_null("pcm");
     if (!enhanced_pcm) return fail_null("enhanced_pcm");
     if (num_frames < 0) return fail(PV_STATUS_INVALID_ARGUMENT, {tag(kCodeGeneric, "`num_frames` must not be negative.")});
+    if (num_frames == 0) return PV_STATUS_SUCCESS;   // nothing to do, host or device buffers alike
     cudaSetDevice(object->engine->device());
     const int kin = pointer_kind(pcm), kout = pointer_kind(enhanced_pcm);
     if (kin != kout) return fail(PV_STATUS_INVALID_ARGUMENT, {tag(kCodeGeneric, "`pcm` and `enhanced_pcm` must both be host or both be device memory.")});
@@ -409,6 +413,13 @@ PV_API pv_status_t pv_koala_batch_num_streams(const pv_koala_batch_t *object, in
     if (!object) return fail_null("object");
     if (!num_streams) return fail_null("num_streams");
     *num_streams = object->engine->num_streams();
+    return PV_STATUS_SUCCESS;
+}
+
+PV_API pv_status_t pv_koala_batch_device(const pv_koala_batch_t *object, int32_t *device_index) {
+    if (!object) return fail_null("object");
+    if (!device_index) return fail_null("device_index");
+    *device_index = object->engine->device();
     return PV_STATUS_SUCCESS;
 }
 
