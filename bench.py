@@ -9,11 +9,13 @@ A "step" is one pass of the hot path over one batch: one 256-sample frame for ev
 configs[3] ("65 536 streams sharded 8xB200"): 8192 streams per GPU, bf16 tensor-core mask estimator, weak scaling, no
 data-path collective -- at N = 8 it is exactly that config.  `value` times the steps with PCM already resident in HBM;
 `e2e` times the same metric through the public API with pinned HOST buffers (H2D + D2H inside the timed region).
+At N = 1 the other BASELINE workloads are measured too (shorter runs) and reported under `others`.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -27,12 +29,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (streams per GPU, precision, description)
-    "cfg4_8192_per_gpu_bf16": (8192, "bf16", "BASELINE configs[3] per-GPU partition: 8192 concurrent 16 kHz streams/GPU, bf16 tcgen05 mask estimator"),
-    "cfg3_4096_bf16": (4096, "bf16", "BASELINE configs[2]: 4096 concurrent streams, 1xB200, bf16 tensor-core mask-estimator GEMMs"),
-    "cfg2_256_fp32": (256, "fp32", "BASELINE configs[1]: 256 concurrent streams, 1xB200, fp32 mask path"),
-    "cfg5_128_per_gpu_bf16": (128, "bf16", "BASELINE configs[4] per-GPU partition: 128 streams/GPU, state carried across calls"),
+    # name: streams per GPU, precision, frames per process() call, description
+    "cfg4_8192_per_gpu_bf16": dict(streams=8192, precision="bf16", frames_per_call=1,
+                                   desc="BASELINE configs[3] per-GPU partition: 8192 concurrent 16 kHz streams/GPU, bf16 tcgen05 mask estimator"),
+    "cfg3_4096_bf16": dict(streams=4096, precision="bf16", frames_per_call=1,
+                           desc="BASELINE configs[2]: 4096 concurrent streams, 1xB200, bf16 tensor-core mask-estimator GEMMs"),
+    "cfg2_256_fp32": dict(streams=256, precision="fp32", frames_per_call=64,
+                          desc="BASELINE configs[1]: 256 concurrent streams, 1xB200, fp32 mask path, fed 64 frames per process() call"),
+    "cfg5_128_per_gpu_bf16": dict(streams=128, precision="bf16", frames_per_call=64,
+                                  desc="BASELINE configs[4] per-GPU partition: 128 streams/GPU (1024 over 8 GPUs), 10-minute clips fed in "
+                                       "64-frame process() calls with the state carried across calls"),
 }
+DEFAULT_WORKLOAD = "cfg4_8192_per_gpu_bf16"
 FRAME = 256
 HIDDEN, LAYERS, BINS = 512, 2, 256
 MACS_PER_FRAME = BINS * HIDDEN + LAYERS * 2 * 3 * HIDDEN * HIDDEN + HIDDEN * BINS      # 3 407 872
@@ -40,11 +48,33 @@ FLOPS_PER_FRAME = 2 * MACS_PER_FRAME                                            
 GRU_FLOPS_PER_STREAM = 2 * 2 * 3 * HIDDEN * HIDDEN                                     # one GRU layer launch, per stream
 STATE_BYTES = 512 + 1024 + LAYERS * HIDDEN * 4                                         # tail + OLA + fp32 h
 BYTES_PER_FRAME = 1024 + 2 * STATE_BYTES
+BURST_MAX_SECONDS = 1.0      # a timed region shorter than this is a burst: compare with the burst peak, else with the sustained one
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
-# of this workload (fused kernel, profiles/r01d_step_ncu_full_selected_metrics.csv); other workloads have no capture -> null
-NCU_DRAM_TRAFFIC_BYTES = {"cfg4_8192_per_gpu_bf16": 61.4e6 + 16.9e6}
+def source_hash() -> str:
+    """Identifies the kernel sources a profile belongs to (profiles/traffic.json is keyed by it)."""
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "koala_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep).  Returns (bytes | None, provenance)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return None, "no profiles/traffic.json"
+    e = t.get(workload)
+    if not e:
+        return None, "no ncu capture of this workload in profiles/traffic.json"
+    same = e.get("source_hash") == source_hash()
+    return e["dram_bytes_per_launch"], f"{e.get('source', 'profiles/traffic.json')} ({'same kernel sources' if same else 'captured on OLDER kernel sources'})"
 
 
 def synth_pcm(n_streams: int, n_frames: int, seed: int) -> np.ndarray:
@@ -116,10 +146,10 @@ class ClockSampler:
         if t_begin is not None and rows:
             inside = [r for r in rows if t_begin - 0.03 <= r[0] <= t_end + 0.03]
             rows = inside if inside else [min(rows, key=lambda r: abs(r[0] - 0.5 * (t_begin + t_end)))]
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for _, r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
@@ -127,7 +157,8 @@ class ClockSampler:
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": float(max(pw))}
 
 
 def cpu_baseline(model_path: str, precision: str, seconds: float, threads: int, streams: int):
@@ -146,12 +177,34 @@ def cpu_baseline(model_path: str, precision: str, seconds: float, threads: int, 
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the reference's own CPU implementation cannot run (closed binary, AccessKey + licence server
-    needed), so this arm times the oracle port on all host threads, per the tier contract."""
+    """--impl reference: times the reference's own CPU engine when it can run here (PV_ACCESS_KEY set, reference checkout present,
+    licence server reachable: tools/record_reference.py), `kind: "reference"`.  Otherwise -- always, in the build container and on
+    the GPU box: the engine is a closed binary that validates an AccessKey online -- the CPU oracle port on all
+    host threads, `kind: "port"`, per the tier contract."""
     if rank != 0:
         return
-    streams_gpu, precision, desc = WORKLOADS[args.workload]
+    w = WORKLOADS[args.workload]
+    streams_gpu, precision, desc = w["streams"], w["precision"], w["desc"]
     threads = os.cpu_count() or 1
+    base = {"impl": "reference", "metric": "enhanced_frames_per_second", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic"}
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import record_reference
+        ref, why = record_reference.time_reference("cpu", max(1, args.steps))
+    except Exception as e:          # the recorder must never take the arm down
+        ref, why = None, repr(e)
+    if ref is not None:
+        value = ref["frames_per_second"]
+        sample = (f"reference engine {ref['version']} (lib/linux/x86_64/libpv_koala.so), device=cpu ({threads} host threads), "
+                  f"{args.steps} passes over test.wav ({ref['frames_per_pass']} frames), bare pv_koala_process loop")
+        line = dict(base, value=value, ms_per_step=1e3 * ref["seconds_per_pass"],
+                    config={"workload": args.workload, "description": desc, "streams_per_gpu": streams_gpu, "frame_length": FRAME,
+                            "note": "single-stream reference engine; a step = one pass over the fixture WAV"},
+                    rtf_x=value * 0.016, cpu_baseline={"value": value, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": sample},
+                    e2e={"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
     sample_streams = min(streams_gpu, max(threads * 8, 64))
     from oracle import OracleBatch, OracleModel, build_oracle
     build_oracle()
@@ -170,21 +223,165 @@ def run_reference(args, rank: int):
     dt = time.perf_counter() - t0
     value = args.steps * sample_streams * frames_per_step / dt
     sample = f"each step = {sample_streams} streams x {frames_per_step} frames of the workload on {threads} host threads (C oracle port)"
-    line = {
-        "impl": "reference", "metric": "enhanced_frames_per_second", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "streams_per_gpu": streams_gpu, "frame_length": FRAME,
-                   "note": "reference engine unrunnable here (closed binary + licence key); CPU oracle port timed instead"},
-        "rtf_x": value * 0.016,
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    line = dict(base, value=value, ms_per_step=1e3 * dt / args.steps,
+                config={"workload": args.workload, "description": desc, "streams_per_gpu": streams_gpu, "frame_length": FRAME,
+                        "note": "reference engine unrunnable here (%s); CPU oracle port timed instead" % why},
+                rtf_x=value * 0.016, cpu_baseline={"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+                e2e={"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(line), flush=True)
     try:
         os.remove(model)
     except OSError:
         pass
+
+
+class Runner:
+    """One workload on this rank's GPU: device-resident timing, per-kernel timing, end-to-end timing through host buffers."""
+
+    def __init__(self, name, streams, model, local_rank, world, total_streams=None):
+        import torch
+        import koala_b200 as kb
+        w = WORKLOADS[name]
+        self.name, self.w, self.torch, self.world = name, w, torch, world
+        self.streams, self.precision, self.fpc = streams, w["precision"], w["frames_per_call"]
+        self.dev = torch.device("cuda", local_rank)
+        if total_streams is None:
+            self.eng = kb.BatchKoala(streams, model_path=model, device=f"gpu:{local_rank}", precision=self.precision)
+        else:       # under torchrun: the product's multi-GPU front door owns the partition
+            self.sharded = kb.ShardedKoala(total_streams, model_path=model, precision=self.precision)
+            assert self.sharded.num_streams == streams
+            self.eng = self.sharded.engine
+        self.stream = torch.cuda.Stream(self.dev)        # the launching stream: kernels AND timing events go here
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def setup_ring(self, ring, seed):
+        torch = self.torch
+        self.ring = ring
+        self.host_pcm = synth_pcm(self.streams, ring, seed=seed)           # [B][ring][256]
+        if self.fpc == 1:
+            # time-major [ring][B][256]: each step's frames are one contiguous [B][256] block, exactly what a caller of the
+            # one-frame-per-call API hands over (stream stride 256)
+            self.d_in = torch.from_numpy(np.ascontiguousarray(self.host_pcm.transpose(1, 0, 2))).to(self.dev)
+        else:
+            self.d_in = torch.from_numpy(self.host_pcm).to(self.dev)       # stream-major [B][ring][256]: multi-frame calls
+        self.d_out = torch.empty_like(self.d_in)
+
+    def run_steps(self, first, count):
+        """Enqueues steps [first, first + count) on the launching stream; returns the number of process() calls made."""
+        from ctypes import c_void_p
+        lib, handle, st = self.eng._library, self.eng._handle, c_void_p(self.stream.cuda_stream)
+        calls = 0
+        if self.fpc == 1:
+            for i in range(first, first + count):
+                off = (i % self.ring) * self.streams * FRAME * 2           # ring slot = a [B][256] block: frame of stream s at + s*256
+                rc = lib.pv_koala_batch_process_async(handle, self.d_in.data_ptr() + off, self.d_out.data_ptr() + off, 1, FRAME, st)
+                if rc != 0:
+                    raise RuntimeError(f"pv_koala_batch_process_async failed with status {rc}")
+                calls += 1
+            return calls
+        i, end = first, first + count
+        while i < end:
+            t0 = i % self.ring
+            n = min(self.fpc, end - i, self.ring - t0)                     # frames of this call (state carries to the next one)
+            off = t0 * FRAME * 2
+            rc = lib.pv_koala_batch_process_async(handle, self.d_in.data_ptr() + off, self.d_out.data_ptr() + off, n, self.ring * FRAME, st)
+            if rc != 0:
+                raise RuntimeError(f"pv_koala_batch_process_async failed with status {rc}")
+            i += n
+            calls += 1
+        return calls
+
+    def timed(self, steps, warmup, sampler=None):
+        torch = self.torch
+        torch.cuda.set_stream(self.stream)
+        self.run_steps(0, warmup)
+        self.barrier()
+        if sampler:
+            sampler.wait_first()
+        launches0 = self.eng.kernel_launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        t_begin = time.time()
+        ev0.record(self.stream)
+        calls = self.run_steps(warmup, steps)
+        ev1.record(self.stream)
+        self.barrier()
+        clocks = sampler.stop(t_begin, time.time()) if sampler else None
+        return ev0.elapsed_time(ev1), self.eng.kernel_launches - launches0, calls, clocks
+
+    def profile(self, first, steps):
+        self.eng.profile(True)
+        self.run_steps(first, steps)
+        prof = self.eng.profile_read()
+        self.eng.profile(False)
+        return prof
+
+    def e2e(self, e2e_steps, extras=True):
+        """Through the public API with pinned HOST buffers: one call carries e2e_steps frames of every stream in the time-major layout
+        [steps][B][256] (a frame of every stream per 16 ms tick); inside it every step's frames go host -> device and its enhanced
+        frames device -> host, chunk by chunk, overlapped with compute by the library's ingest path.  Wall clock around the call."""
+        torch, eng, ring = self.torch, self.eng, self.ring
+        tm = np.ascontiguousarray(self.host_pcm.transpose(1, 0, 2))        # [ring][B][256]
+        h_in = torch.from_numpy(np.concatenate([tm] * ((e2e_steps + ring - 1) // ring), axis=0)[:e2e_steps]).pin_memory()
+        h_out = torch.empty_like(h_in).pin_memory()
+        eng.process(h_in[:8].contiguous().pin_memory(), out=torch.empty_like(h_in[:8]).pin_memory(), time_major=True)   # warm-up (allocates staging)
+        self.barrier()
+        t0 = time.perf_counter()
+        eng.process(h_in, out=h_out, time_major=True)                 # synchronous: returns when h_out is valid
+        torch.cuda.synchronize(self.dev)
+        seconds = time.perf_counter() - t0
+        res = {"seconds": seconds}
+        if extras:
+            # the same thing one step per call (the latency-bound way to drive the API), for reference
+            h1_in = h_in[0].contiguous().pin_memory()
+            h1_out = torch.empty_like(h1_in).pin_memory()
+            eng.process(h1_in, out=h1_out)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                eng.process(h1_in, out=h1_out)
+            res["one_step_per_call_fps"] = self.streams * 20 / (time.perf_counter() - t0)
+            # ... and one call in the stream-major layout [B][steps][256] (pitched copies, wide output blocks)
+            s_in = torch.from_numpy(np.ascontiguousarray(h_in.numpy().transpose(1, 0, 2))).pin_memory()
+            s_out = torch.empty_like(s_in).pin_memory()
+            eng.process(s_in, out=s_out)                                  # sizes the staging buffers for this layout
+            t0 = time.perf_counter()
+            eng.process(s_in, out=s_out)
+            torch.cuda.synchronize(self.dev)
+            res["stream_major_call_fps"] = self.streams * e2e_steps / (time.perf_counter() - t0)
+        return res
+
+    def close(self):
+        self.eng.delete()
+
+
+def roofline_of(name, streams, precision, prof, prof_steps, timed_seconds, peaks):
+    """The roofline object of the dominant kernel: algorithmic flops per launch / its CUDA-event duration against the measured peak."""
+    fused = prof["masknet"][1] > 0                               # encoder -> GRU layers -> decoder in ONE kernel
+    dom_ms, dom_n = prof["masknet"] if fused else prof["gru"]
+    dom_flops = (FLOPS_PER_FRAME if fused else GRU_FLOPS_PER_STREAM) * streams * (prof_steps / max(dom_n, 1) if fused else 1.0)
+    tot = max(sum(v[0] for v in prof.values()), 1e-12)
+    shares = {k: v[0] / tot for k, v in prof.items()}
+    burst = timed_seconds < BURST_MAX_SECONDS
+    key = "bf16_tflops" if burst else "bf16_tflops_sustained"
+    if peaks.get(key):
+        peak, src = peaks[key], f"MEASURED_PEAKS.json {key} (timed region {timed_seconds * 1e3:.1f} ms: a {'burst' if burst else 'seconds-long run'}), of measured"
+    else:
+        peak, src = (1590.0, "fallback 1.59 PFLOP/s burst (B200_PROFILING.md), of fallback") if burst else (1400.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md), of fallback")
+    achieved = dom_flops / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 if dom_n else None
+    traffic, traffic_src = ncu_traffic(name) if streams == WORKLOADS[name]["streams"] else (None, "stream count overridden")
+    kernel = ("tc_fused_kernel (encoder + GRU layers + decoder GEMMs, all streams" + ("" if prof_steps == dom_n else f", {prof_steps // max(dom_n, 1)} steps per launch") + ")") if fused \
+        else "gru_fp32_kernel (CUDA-core FMA GRU layer)"
+    r = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": src,
+         "avg_launch_ms": dom_ms / max(dom_n, 1), "algorithmic_flops_per_launch": dom_flops, "kernel_share_of_step": shares,
+         "note": "launch duration from CUDA events bracketing the kernel; bracketing disables the dependent-launch overlap with the "
+                 "neighbouring kernels, so the bracketed durations sum to more than ms_per_step"}
+    return r
 
 
 def main():
@@ -193,12 +390,13 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg4_8192_per_gpu_bf16", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
     ap.add_argument("--ring-frames", type=int, default=64, help="distinct input frames per stream kept in HBM")
     ap.add_argument("--e2e-steps", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE workloads (measured at N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -211,107 +409,36 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import koala_b200 as kb
     from koala_b200 import _build
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
+    _build.build()
+    w = WORKLOADS[args.workload]
+    streams, precision, desc = (args.streams or w["streams"]), w["precision"], w["desc"]
+    model = bench_model_path() if rank == 0 or world == 1 else None
+
+    # CPU baseline first, at N = 1 only, before any GPU work or process group exists: the oracle port on all host threads,
+    # on a bounded sample of the same workload (with other ranks spinning in NCCL barriers the host cores are not free)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import build_oracle
+        build_oracle()
+        threads = os.cpu_count() or 1
+        v, sample = cpu_baseline(model, precision, args.cpu_seconds, threads, min(streams, max(64, threads * 8)))
+        cpu = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
+               "note": "reference CPU engine not measurable (closed binary, needs AccessKey + licence server); "
+                       "its CI ceilings: >456 frames/s cpu:1 on GitHub runners (BASELINE.md section 1)"}
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)   # NCCL only for barriers / reductions of timings: no data-path collective
-    _build.build()
+        box = [model]
+        dist.broadcast_object_list(box, src=0)           # every rank reads the same model file (one node)
+        model = box[0]
 
-    streams, precision, desc = WORKLOADS[args.workload]
-    if args.streams:
-        streams = args.streams
-    model = bench_model_path()
-    eng = kb.BatchKoala(streams, model_path=model, device=f"gpu:{local_rank}", precision=precision)
-
-    ring = args.ring_frames
-    host_pcm = synth_pcm(streams, ring, seed=0x4B4F414C + rank)
-    # resident in HBM, time-major [ring][B][256]: each step's frames are one contiguous [B][256] block, exactly what a
-    # caller of the one-frame-per-call API hands over (stream stride 256)
-    d_in = torch.from_numpy(np.ascontiguousarray(host_pcm.transpose(1, 0, 2))).to(dev)
-    d_out = torch.empty_like(d_in)
-    stream = torch.cuda.Stream(dev)                                # the launching stream: kernels AND timing events go here
-    torch.cuda.set_stream(stream)
-    lib, handle = eng._library, eng._handle
-    from ctypes import c_void_p
-
-    def step(i):
-        off = (i % ring) * streams * FRAME * 2                     # ring slot = a [B][256] block: frame of stream s at + s*256
-        rc = lib.pv_koala_batch_process_async(handle, d_in.data_ptr() + off, d_out.data_ptr() + off, 1, FRAME,
-                                              c_void_p(stream.cuda_stream))
-        if rc != 0:
-            raise RuntimeError(f"pv_koala_batch_process_async failed with status {rc}")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    sampler.wait_first()
-    launches0 = eng.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_begin = time.time()
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop(t_begin, time.time())
-    ms_local = ev0.elapsed_time(ev1)
-    launches_local = eng.kernel_launches - launches0
-
-    # ---- per-kernel-class timing with CUDA events on the launching stream (dominant kernel -> roofline)
-    eng.profile(True)
-    prof_steps = min(args.steps, 100)
-    for i in range(prof_steps):
-        step(args.warmup + args.steps + i)
-    prof = eng.profile_read()
-    eng.profile(False)
-
-    # ---- end to end through the public API with pinned HOST buffers: one call carries e2e_steps frames of every stream in the
-    # time-major layout [steps][B][256] (a frame of every stream per 16 ms tick); inside it every step's 256-sample frames go
-    # host -> device and its enhanced frames device -> host, chunk by chunk, overlapped with compute by the library's ingest
-    # path.  Timed by wall clock around the synchronous call.
-    e2e_steps = max(8, args.e2e_steps)
-    tm = np.ascontiguousarray(host_pcm.transpose(1, 0, 2))        # [ring][B][256]
-    h_in = torch.from_numpy(np.concatenate([tm] * ((e2e_steps + ring - 1) // ring), axis=0)[:e2e_steps]).pin_memory()
-    h_out = torch.empty_like(h_in).pin_memory()
-    eng.process(h_in[:8].contiguous().pin_memory(), out=torch.empty_like(h_in[:8]).pin_memory(), time_major=True)   # warm-up (allocates staging)
-    barrier()
-    t0 = time.perf_counter()
-    eng.process(h_in, out=h_out, time_major=True)                 # synchronous: returns when h_out is valid
-    torch.cuda.synchronize(dev)
-    e2e_s_local = time.perf_counter() - t0
-    # the same thing one step per call (the latency-bound way to drive the API), for reference
-    h1_in = h_in[0].contiguous().pin_memory()
-    h1_out = torch.empty_like(h1_in).pin_memory()
-    eng.process(h1_in, out=h1_out)
-    t0 = time.perf_counter()
-    for i in range(20):
-        eng.process(h1_in, out=h1_out)
-    e2e_single_call_fps = streams * 20 / (time.perf_counter() - t0)
-    # ... and one call in the stream-major layout [B][steps][256] (pitched copies, wide output blocks)
-    s_in = torch.from_numpy(np.ascontiguousarray(h_in.numpy().transpose(1, 0, 2))).pin_memory()
-    s_out = torch.empty_like(s_in).pin_memory()
-    eng.process(s_in, out=s_out)                                  # sizes the staging buffers for this layout
-    t0 = time.perf_counter()
-    eng.process(s_in, out=s_out)
-    torch.cuda.synchronize(dev)
-    e2e_stream_major_fps = streams * e2e_steps / (time.perf_counter() - t0)
-    del s_in, s_out
-
-    # ---- reduce over ranks: SUM of units, MAX of time
     def reduce(v, op):
         if world == 1:
             return v
@@ -320,63 +447,76 @@ def main():
         return t.item()
 
     SUM, MAX = (dist.ReduceOp.SUM, dist.ReduceOp.MAX) if world > 1 else (None, None)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+
+    run = Runner(args.workload, streams, model, local_rank, world, total_streams=streams * world if world > 1 else None)
+    run.setup_ring(args.ring_frames, seed=0x4B4F414C + rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_local, launches_local, calls_local, clocks = run.timed(args.steps, args.warmup, sampler)
+    prof_steps = min(args.steps, 128) // w["frames_per_call"] * w["frames_per_call"] or min(args.steps, 128)
+    prof = run.profile(args.warmup + args.steps, prof_steps)
+    e2e_steps = max(8, args.e2e_steps)
+    e2e = run.e2e(e2e_steps)
+
     ms = reduce(ms_local, MAX)
     total_frames = reduce(streams * args.steps, SUM)
-    e2e_s = reduce(e2e_s_local, MAX)
+    e2e_s = reduce(e2e["seconds"], MAX)
     e2e_frames = reduce(streams * e2e_steps, SUM)
     launches = int(reduce(launches_local, SUM))
     value = total_frames / (ms * 1e-3)
     e2e_value = e2e_frames / e2e_s
+    run.close()
+
+    others = None
+    if world == 1 and not args.no_others and not args.streams and args.workload == DEFAULT_WORKLOAD:
+        # the other BASELINE workloads, same build, shorter runs: one compact line each (device-resident value, end-to-end value,
+        # the dominant kernel's roofline fraction)
+        others = {}
+        for name, ow in WORKLOADS.items():
+            if name == args.workload:
+                continue
+            try:
+                r = Runner(name, ow["streams"], model, local_rank, 1)
+                r.setup_ring(args.ring_frames, seed=0x4B4F414C)
+                o_steps = max(ow["frames_per_call"] * 4, min(args.steps, 512))
+                o_ms, o_launches, o_calls, _ = r.timed(o_steps, max(args.warmup, ow["frames_per_call"]))
+                o_prof_steps = max(ow["frames_per_call"], 64)
+                o_prof = r.profile(o_steps, o_prof_steps)
+                o_e2e = r.e2e(max(8, min(e2e_steps, 64)), extras=False)
+                o_value = ow["streams"] * o_steps / (o_ms * 1e-3)
+                roof = roofline_of(name, ow["streams"], ow["precision"], o_prof, o_prof_steps, o_ms * 1e-3, peaks)
+                others[name] = {"description": ow["desc"], "value": o_value, "unit": "frames/s", "steps": o_steps, "ms_per_step": o_ms / o_steps,
+                                "frames_per_call": ow["frames_per_call"], "process_calls": o_calls, "gpu_launches": o_launches,
+                                "dtype": ow["precision"], "rtf_x": o_value * 0.016,
+                                "rtf_x_at_8_gpus_if_linear": o_value * 0.016 * 8,
+                                "e2e": {"value": ow["streams"] * max(8, min(e2e_steps, 64)) / o_e2e["seconds"], "unit": "frames/s",
+                                        "h2d_bytes_per_step": ow["streams"] * FRAME * 2, "d2h_bytes_per_step": ow["streams"] * FRAME * 2},
+                                "roofline": {k: roof[k] for k in ("kernel", "achieved", "peak", "frac", "avg_launch_ms", "peak_source")}}
+                r.close()
+            except Exception as e:      # a side workload must never take the headline line down
+                others[name] = {"error": repr(e)[:300]}
 
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except OSError:
-            pass
-        fused = precision == "bf16"                            # bf16 path: encoder -> GRU layers -> decoder in ONE kernel
-        gru_ms, gru_n = prof["masknet"] if fused else prof["gru"]   # fp32 path: the GRU layer kernel dominates
-        dom_flops = (FLOPS_PER_FRAME if fused else GRU_FLOPS_PER_STREAM) * streams
+        roofline = roofline_of(args.workload, streams, precision, prof, prof_steps, ms * 1e-3, peaks)
         step_prof_ms = sum(v[0] for v in prof.values()) / max(prof_steps, 1)
-        shares = {k: (v[0] / max(sum(x[0] for x in prof.values()), 1e-12)) for k, v in prof.items()}
-        if precision == "bf16":
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-            achieved = dom_flops / (gru_ms / max(gru_n, 1) * 1e-3) / 1e12 if gru_n else None
-            roofline = {"bound": "tensor", "kernel": "tc_fused_kernel (encoder + GRU layers + decoder GEMMs of one step, all streams)", "achieved": achieved,
-                        "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                        "traffic": NCU_DRAM_TRAFFIC_BYTES.get(args.workload) if not args.streams else None,
-                        "peak_source": peak_src, "avg_launch_ms": gru_ms / max(gru_n, 1),
-                        "algorithmic_flops_per_launch": dom_flops}
-        else:
-            # fp32 CUDA-core path: no measured fp32 peak in MEASURED_PEAKS.json; nominal 148 SM x 128 FMA x 2 x sm_max_mhz
-            peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
-            achieved = GRU_FLOPS_PER_STREAM * streams / (gru_ms / max(gru_n, 1) * 1e-3) / 1e12 if gru_n else None
-            roofline = {"bound": "tensor", "kernel": "gru_fp32_kernel (CUDA-core FMA; bound is the fp32 FMA pipe, not the tensor pipe)",
-                        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                        "traffic": None, "peak_source": "nominal fp32 FMA peak at clocks.max.sm (no measured fp32 figure)",
-                        "avg_launch_ms": gru_ms / max(gru_n, 1), "algorithmic_flops_per_launch": GRU_FLOPS_PER_STREAM * streams}
-        roofline["kernel_share_of_step"] = shares
-        roofline["step_tensor_frac"] = (value / world) * FLOPS_PER_FRAME / 1e12 / (peaks.get("bf16_tflops_sustained", 1400.0))
+        step_peak = roofline["peak"]
+        roofline["step_tensor_frac"] = (value / world) * FLOPS_PER_FRAME / 1e12 / step_peak
         roofline["step_hbm_frac"] = (value / world) * BYTES_PER_FRAME / 1e9 / (peaks.get("hbm_gbs", 6650.0))
-        cpu = None
-        if not args.no_cpu_baseline:
-            from oracle import build_oracle
-            build_oracle()
-            threads = os.cpu_count() or 1
-            v, sample = cpu_baseline(model, precision, args.cpu_seconds, threads, min(streams, max(64, threads * 8)))
-            cpu = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
-                   "note": "reference CPU engine not measurable (closed binary, needs AccessKey + licence server); "
-                           "its CI ceilings: >456 frames/s cpu:1 on GitHub runners (BASELINE.md section 1)"}
         line = {
             "metric": "enhanced_frames_per_second", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": precision, "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "streams_per_gpu": streams, "total_streams": streams * world,
                        "frame_length": FRAME, "sample_rate": 16000, "hidden": HIDDEN, "gru_layers": LAYERS,
-                       "parallelism": f"stream-partition x{world} (no data-path collective)",
-                       "l2": f"input/output rings of {ring} frames/stream = {2 * streams * ring * FRAME * 2 / 2**20:.0f} MiB (> 126 MB L2 at the "
+                       "frames_per_process_call": w["frames_per_call"],
+                       "parallelism": f"stream-partition x{world} (koala_b200.ShardedKoala, no data-path collective)" if world > 1 else "one GPU",
+                       "l2": f"input/output rings of {args.ring_frames} frames/stream = {2 * streams * args.ring_frames * FRAME * 2 / 2**20:.0f} MiB (> 126 MB L2 at the "
                              f"default size); per-stream recurrent state is re-read every step by construction",
                        "weights": "random-init, seeded (koala_b200.spec.random_model)"},
             "rtf_x": value * 0.016, "rtf_reference_convention": 1.0 / (value * 0.016),
@@ -386,19 +526,20 @@ def main():
                     "d2h_bytes_per_step": streams * FRAME * 2, "steps": e2e_steps,
                     "api": "koala_b200.BatchKoala.process(pinned host tensor [steps][B][256], time_major=True) -> "
                            "pv_koala_batch_process_time_major, one call",
-                    "one_step_per_call_value_rank0": e2e_single_call_fps, "stream_major_call_value_rank0": e2e_stream_major_fps},
+                    "one_step_per_call_value_rank0": e2e.get("one_step_per_call_fps"), "stream_major_call_value_rank0": e2e.get("stream_major_call_fps")},
             "gpu_launches": launches,
+            "process_calls": calls_local,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernel_ms_per_step": {k: v[0] / max(prof_steps, 1) for k, v in prof.items()},
             "profiled_step_ms": step_prof_ms,
+            "others": others,
         }
         print(json.dumps(line), flush=True)
-    try:
-        os.remove(model)
-    except OSError:
-        pass
-    eng.delete()
+        try:
+            os.remove(model)
+        except OSError:
+            pass
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -387,6 +387,7 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     const int stft_per_warp = p->stft_per_warp > 0 ? p->stft_per_warp : std::max(1, B / resident_warps);
     const int stft_grid = std::max(1, (B + kStftWarps * stft_per_warp - 1) / (kStftWarps * stft_per_warp));
     KernelProfiler *prof = p->prof;
+    static const bool only_masknet = [] { const char *e = getenv("KOALA_B200_ONLY_MASKNET"); return e && e[0] == '1'; }();
     for (int t = 0; t < frames; t++) {
         PcmView v{pcm, out, stride, out_stride, t};
         const int cur = p->parity, nxt = cur ^ 1;
@@ -409,6 +410,12 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
             launch_pdl(false, linear_fp32_kernel<kActSigmoid>, dim3(Bp / kF32Bm, kBins / kF32LinN), dim3(256), 0, st, x, p->dec_w, p->dec_b, p->mask, H, kBins);
             if (prof) prof->end(st);
             launches_ += 3 + L;
+        } else if (only_masknet) {      // tuning aid (KOALA_B200_ONLY_MASKNET=1): the fused kernel alone, back to back, on stale features
+            if (prof) prof->begin(kKernMasknet, st);
+            launches_ += fu_masknet_step(p->fu, cur, st);
+            if (prof) prof->end(st);
+            p->parity = nxt;
+            continue;
         } else {
             if (prof) prof->begin(kKernFrontend, st);
             launch_pdl(true, frontend_kernel<__nv_bfloat16>, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->tail, p->spec,
