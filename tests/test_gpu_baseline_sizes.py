@@ -80,36 +80,52 @@ def test_baseline_config_sizes_against_oracle(library_path, random_model_path, n
     eng.delete()
 
 
-def test_full_scale_inputs_residual_is_quantified(library_path, random_model_path):
-    """bf16 mode, +-32767 full-scale inputs: an activation operand that sits within ~1e-6 of a bf16 rounding boundary can round
-    the other way on the GPU than in the oracle (fp32 summation order differs); that moves the mask by ~3e-5, which is 1 LSB
-    only where |x| ~ 32767.  Measured here over >= 10^6 samples so that SPEC.md section 4 states a bound instead of an
-    anecdote: at most 2 LSB, on under 10 % of the samples."""
-    n, frames = 64, 64
-    rng = np.random.default_rng(11)
+def full_scale_pcm(n, frames, seed=11):
+    """+-32767 adversarial inputs: square waves, clipped sines, full-scale binary noise, DC rails."""
+    rng = np.random.default_rng(seed)
     k = np.arange(frames * 256)
     pcm = np.empty((n, frames * 256), np.int16)
     for s in range(n):
         period = int(rng.integers(2, 200))
         kind = s % 4
         if kind == 0:
-            pcm[s] = np.where((k // period) % 2 == 0, 32767, -32768)                        # square waves
+            pcm[s] = np.where((k // period) % 2 == 0, 32767, -32768)
         elif kind == 1:
-            pcm[s] = np.clip(np.rint(40000.0 * np.sin(2 * np.pi * k / (period + 2.5))), -32768, 32767)   # clipped sines
+            pcm[s] = np.clip(np.rint(40000.0 * np.sin(2 * np.pi * k / (period + 2.5))), -32768, 32767)
         elif kind == 2:
-            pcm[s] = np.where(rng.random(k.size) < 0.5, 32767, -32768)                      # full-scale noise
+            pcm[s] = np.where(rng.random(k.size) < 0.5, 32767, -32768)
         else:
-            pcm[s] = 32767 if s % 8 == 3 else -32768                                        # DC rails
-    pcm = pcm.reshape(n, frames, 256)
-    eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
-    out = eng.process(pcm)
-    ref = OracleBatch(OracleModel(random_model_path), n, "bf16").process(pcm, threads=os.cpu_count() or 8)
-    hist = lsb_histogram(out, ref)
-    frac2 = sum(v for k_, v in hist["hist"].items() if int(k_) >= 2) / hist["samples"]
-    dump("parity_hist_full_scale_bf16.json", {"streams": n, "frames": frames, "fraction_ge_2_lsb": frac2, **hist})
-    assert hist["samples"] >= 10 ** 6
-    assert hist["max"] <= 2 and frac2 < 0.10, (hist, frac2)
-    eng.delete()
+            pcm[s] = 32767 if s % 8 == 3 else -32768
+    return pcm.reshape(n, frames, 256)
+
+
+def test_full_scale_inputs_residual_is_quantified(library_path, random_model_path):
+    """What the +-1 LSB bar means at +-32767 full scale (SPEC.md section 4), measured over > 10^6 samples per mode.
+
+    fp32 mode: GPU and oracle masks agree to ~1e-6, so the int16 output stays within +-1 LSB at any level -- asserted.
+    bf16 mode: both sides round every GEMM operand to bf16, but from fp32 values that differ in the last bits (summation
+    order, FFT schedule, transcendental approximations), so now and then an operand lands on the other side of a bf16 rounding
+    boundary (~0.5 per stream-step).  One such flip moves the mask by ~3e-5; carried through the recurrent state over 64 steps the
+    masks differ by up to ~2.5e-4 absolute -- well inside the 1e-3 mask tolerance, invisible (< 1 LSB) for |x| < ~4000 (every
+    BASELINE workload: max 1 LSB, 99.7 % exact, test above), but up to |x| * 2.5e-4 = 8 LSB at the rails.  Asserted bound:
+    |cuda - oracle| <= 1 + 2.5e-4 * 32768 = 9 LSB, and at most 1 LSB on at least 80 % of the samples."""
+    n, frames = 64, 64
+    pcm = full_scale_pcm(n, frames)
+    for precision, max_lsb in (("fp32", 1), ("bf16", 9)):
+        eng = kb.BatchKoala(n, model_path=random_model_path, precision=precision)
+        out = eng.process(pcm)
+        ob = OracleBatch(OracleModel(random_model_path), n, precision)
+        ref = ob.process(pcm, threads=os.cpu_count() or 8)
+        hist = lsb_histogram(out, ref)
+        frac2 = sum(v for k_, v in hist["hist"].items() if int(k_) >= 2) / hist["samples"]
+        mask = eng.debug_read("mask", (n, 256), np.float32)
+        dmask = float(np.abs(mask - np.stack([ob.stream(s).last_mask for s in range(n)])).max())
+        dump(f"parity_hist_full_scale_{precision}.json", {"streams": n, "frames": frames, "fraction_ge_2_lsb": frac2,
+                                                          "max_abs_mask_difference_last_step": dmask, **hist})
+        assert hist["samples"] >= 10 ** 6
+        assert hist["max"] <= max_lsb and frac2 < 0.20, (precision, hist, frac2)
+        assert dmask < (1e-5 if precision == "fp32" else 1e-3), (precision, dmask)
+        eng.delete()
 
 
 def test_config5_shape_state_carry_in_chunks(library_path, shipped_model_path):
