@@ -7,7 +7,10 @@
 A "step" is one pass of the hot path over one batch: one 256-sample frame for every stream resident on the GPU
 (analysis/STFT -> mask estimator -> synthesis/iSTFT).  Default workload = the per-GPU partition of BASELINE.json
 configs[3] ("65 536 streams sharded 8xB200"): 8192 streams per GPU, bf16 tensor-core mask estimator, weak scaling, no
-data-path collective -- at N = 8 it is exactly that config.  `value` times the steps with PCM already resident in HBM;
+data-path collective -- at N = 8 it is exactly that config.  The steps are fed `frames_per_process_call` frames per call
+(the library walks a call's frames in chunks: analysis of the chunk, ONE persistent mask-estimator launch stepping through
+its frames, synthesis of the chunk); the one-frame-per-call rate is reported beside it (`one_frame_per_call`).  `value` times
+the steps with PCM already resident in HBM;
 `e2e` times the same metric through the public API with pinned HOST buffers (H2D + D2H inside the timed region).
 At N = 1 the other BASELINE workloads are measured too (shorter runs) and reported under `others`.
 Prints ONE JSON line on rank 0.
@@ -30,9 +33,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: streams per GPU, precision, frames per process() call, description
-    "cfg4_8192_per_gpu_bf16": dict(streams=8192, precision="bf16", frames_per_call=1,
+    "cfg4_8192_per_gpu_bf16": dict(streams=8192, precision="bf16", frames_per_call=16, time_major=True,
                                    desc="BASELINE configs[3] per-GPU partition: 8192 concurrent 16 kHz streams/GPU, bf16 tcgen05 mask estimator"),
-    "cfg3_4096_bf16": dict(streams=4096, precision="bf16", frames_per_call=1,
+    "cfg3_4096_bf16": dict(streams=4096, precision="bf16", frames_per_call=32, time_major=True,
                            desc="BASELINE configs[2]: 4096 concurrent streams, 1xB200, bf16 tensor-core mask-estimator GEMMs"),
     "cfg2_256_fp32": dict(streams=256, precision="fp32", frames_per_call=64,
                           desc="BASELINE configs[1]: 256 concurrent streams, 1xB200, fp32 mask path, fed 64 frames per process() call"),
@@ -244,6 +247,7 @@ class Runner:
         w = WORKLOADS[name]
         self.name, self.w, self.torch, self.world = name, w, torch, world
         self.streams, self.precision, self.fpc = streams, w["precision"], w["frames_per_call"]
+        self.time_major = bool(w.get("time_major")) or self.fpc == 1
         self.dev = torch.device("cuda", local_rank)
         if total_streams is None:
             self.eng = kb.BatchKoala(streams, model_path=model, device=f"gpu:{local_rank}", precision=self.precision)
@@ -263,9 +267,9 @@ class Runner:
         torch = self.torch
         self.ring = ring
         self.host_pcm = synth_pcm(self.streams, ring, seed=seed)           # [B][ring][256]
-        if self.fpc == 1:
-            # time-major [ring][B][256]: each step's frames are one contiguous [B][256] block, exactly what a caller of the
-            # one-frame-per-call API hands over (stream stride 256)
+        if self.time_major:
+            # time-major [ring][B][256]: each step's frames are one contiguous [B][256] block, what a caller that collects one
+            # frame of every stream per 16 ms tick has (stream stride 256, frame stride B * 256)
             self.d_in = torch.from_numpy(np.ascontiguousarray(self.host_pcm.transpose(1, 0, 2))).to(self.dev)
         else:
             self.d_in = torch.from_numpy(self.host_pcm).to(self.dev)       # stream-major [B][ring][256]: multi-frame calls
@@ -276,20 +280,17 @@ class Runner:
         from ctypes import c_void_p
         lib, handle, st = self.eng._library, self.eng._handle, c_void_p(self.stream.cuda_stream)
         calls = 0
-        if self.fpc == 1:
-            for i in range(first, first + count):
-                off = (i % self.ring) * self.streams * FRAME * 2           # ring slot = a [B][256] block: frame of stream s at + s*256
-                rc = lib.pv_koala_batch_process_async(handle, self.d_in.data_ptr() + off, self.d_out.data_ptr() + off, 1, FRAME, st)
-                if rc != 0:
-                    raise RuntimeError(f"pv_koala_batch_process_async failed with status {rc}")
-                calls += 1
-            return calls
         i, end = first, first + count
         while i < end:
             t0 = i % self.ring
             n = min(self.fpc, end - i, self.ring - t0)                     # frames of this call (state carries to the next one)
-            off = t0 * FRAME * 2
-            rc = lib.pv_koala_batch_process_async(handle, self.d_in.data_ptr() + off, self.d_out.data_ptr() + off, n, self.ring * FRAME, st)
+            if self.time_major:                                            # ring slot = a [B][256] block: frame of stream s at + s*256
+                off = t0 * self.streams * FRAME * 2
+                rc = lib.pv_koala_batch_process_async_strided(handle, self.d_in.data_ptr() + off, self.d_out.data_ptr() + off, n, FRAME,
+                                                              self.streams * FRAME, st)
+            else:
+                off = t0 * FRAME * 2
+                rc = lib.pv_koala_batch_process_async(handle, self.d_in.data_ptr() + off, self.d_out.data_ptr() + off, n, self.ring * FRAME, st)
             if rc != 0:
                 raise RuntimeError(f"pv_koala_batch_process_async failed with status {rc}")
             i += n
@@ -461,6 +462,13 @@ def main():
     ms_local, launches_local, calls_local, clocks = run.timed(args.steps, args.warmup, sampler)
     prof_steps = min(args.steps, 128) // w["frames_per_call"] * w["frames_per_call"] or min(args.steps, 128)
     prof = run.profile(args.warmup + args.steps, prof_steps)
+    one_frame = None
+    if w["frames_per_call"] > 1:        # the same steps driven one frame per call (three launches per frame)
+        fpc, run.fpc = run.fpc, 1
+        o_ms, o_launches, _, _ = run.timed(min(args.steps, 256), args.warmup)
+        run.fpc = fpc
+        one_frame = {"value": reduce(streams * min(args.steps, 256), SUM) / (reduce(o_ms, MAX) * 1e-3), "unit": "frames/s",
+                     "ms_per_step": reduce(o_ms, MAX) / min(args.steps, 256), "gpu_launches_rank0": o_launches}
     e2e_steps = max(8, args.e2e_steps)
     e2e = run.e2e(e2e_steps)
 
@@ -529,6 +537,7 @@ def main():
                     "one_step_per_call_value_rank0": e2e.get("one_step_per_call_fps"), "stream_major_call_value_rank0": e2e.get("stream_major_call_fps")},
             "gpu_launches": launches,
             "process_calls": calls_local,
+            "one_frame_per_call": one_frame,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernel_ms_per_step": {k: v[0] / max(prof_steps, 1) for k, v in prof.items()},

@@ -111,6 +111,14 @@ PV_API pv_status_t pv_koala_batch_process_time_major(pv_koala_batch_t *object, c
  * mask-estimator kernel needs its whole grid resident). */
 PV_API pv_status_t pv_koala_batch_process_async(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,
                                                 int32_t num_frames, int64_t stream_stride, void *cuda_stream);
+/* Same with an explicit distance between consecutive frames of one stream: frame t of stream s at
+ * base + s * stream_stride + t * frame_stride samples (time-major device buffers: stream_stride 256, frame_stride
+ * num_streams * 256).  The call's frames are taken in chunks of up to pv_koala_batch_chunk_frames() frames: three kernel
+ * launches per chunk (analysis of the chunk, one persistent mask-estimator launch walking its steps, synthesis), so the
+ * caller's serial frame loop (reference: demo/c/koala_demo_file.c:466-521) costs launches per chunk, not per frame. */
+PV_API pv_status_t pv_koala_batch_process_async_strided(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,
+                                                        int32_t num_frames, int64_t stream_stride, int64_t frame_stride, void *cuda_stream);
+PV_API pv_status_t pv_koala_batch_chunk_frames(const pv_koala_batch_t *object, int32_t *chunk_frames);
 PV_API pv_status_t pv_koala_batch_synchronize(pv_koala_batch_t *object);
 
 /* stream_ids == NULL resets every stream (pv_koala_reset semantics per stream). */

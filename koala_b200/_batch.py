@@ -35,6 +35,10 @@ class BatchKoala(object):
         library.pv_koala_batch_process_time_major.restype = c_int
         library.pv_koala_batch_process_async.argtypes = [H, c_void_p, c_void_p, c_int32, c_int64, c_void_p]
         library.pv_koala_batch_process_async.restype = c_int
+        library.pv_koala_batch_process_async_strided.argtypes = [H, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p]
+        library.pv_koala_batch_process_async_strided.restype = c_int
+        library.pv_koala_batch_chunk_frames.argtypes = [H, POINTER(c_int32)]
+        library.pv_koala_batch_chunk_frames.restype = c_int
         library.pv_koala_batch_synchronize.argtypes = [H]
         library.pv_koala_batch_synchronize.restype = c_int
         library.pv_koala_batch_reset.argtypes = [H, POINTER(c_int32), c_int32]
@@ -61,6 +65,9 @@ class BatchKoala(object):
         self.frame_length = library.pv_koala_frame_length()
         self.sample_rate = library.pv_sample_rate()
         self.delay_sample = 256
+        cf = c_int32(1)
+        check(library, library.pv_koala_batch_chunk_frames(self._handle, byref(cf)), 'chunk_frames failed')
+        self.chunk_frames = cf.value                  # frames one mask-estimator launch walks (bf16 path); 1 for fp32
 
     def delete(self) -> None:
         if self._handle:
@@ -117,11 +124,10 @@ class BatchKoala(object):
                 'Processing failed')
         elif pcm.is_cuda:
             stream = torch.cuda.current_stream(pcm.device).cuda_stream
-            step = self.num_streams * self.frame_length * 2
-            for t in range(frames):     # one enqueue per frame: streams 256 samples apart
-                check(self._library, self._library.pv_koala_batch_process_async(
-                    self._handle, pcm.data_ptr() + t * step, out.data_ptr() + t * step, 1, self.frame_length, c_void_p(stream)),
-                    'Processing failed')
+            # streams 256 samples apart, frames num_streams * 256
+            check(self._library, self._library.pv_koala_batch_process_async_strided(
+                self._handle, pcm.data_ptr(), out.data_ptr(), frames, self.frame_length, self.num_streams * self.frame_length,
+                c_void_p(stream)), 'Processing failed')
         else:
             check(self._library, entry(self._handle, pcm.data_ptr(), out.data_ptr(), frames), 'Processing failed')
         return out

@@ -2,12 +2,15 @@
 //
 // Per-stream state rows (all zero after reset, pv_koala.h:82-90):
 //   tail [Bp][256] int16   previous input frame (analysis overlap)
-//   ola  [Bp][256] fp32    second half of the previous synthesis frame
+//   ola  [Bp][256] fp32    second half of the previous synthesis frame (bf16 path: [2][...] ping-pong by chunk, see backend_kernel)
 //   h    [L][Bp][H] fp32     recurrent state; bf16 path: updated in place, fp32 path: [2][...] ping-pong by step parity
 //   hb   [2][L][Bp][H] bf16  the same state rounded to bf16 = GEMM operand of the tensor-core path, ping-pong by step parity
 //                            (every unit tile reads all of h(t-1))
 // The bf16 path keeps all of the above in one arena (Engine::create).
-// Scratch per step: feat [Bp][256] (fp32 | bf16), spec [Bp][512] fp32, e [Bp][H], mask [Bp][256] fp32.
+// Scratch: feat [T][Bp][256] (fp32 | bf16), spec [T][Bp][512] fp32, mask [T][Bp][256] fp32 for the T frames one chunk of the
+// bf16 path takes through its three launches (analysis of T frames -> fused mask estimator walking T steps -> synthesis of T
+// frames; T = chunk_frames() <= 64, sized so that the scratch stays under 512 MB), e [ring][Bp][H] (encoder output ring of
+// the fused kernel).  The fp32 path works frame by frame in slot 0.
 // Bp = B rounded up to 256 (one CTA-pair tile) so that every GEMM tile is full; padding rows stay zero-input and are
 // never copied out.
 #include "engine.h"
@@ -113,20 +116,24 @@ struct Engine::Impl {
     cudaStream_t stream = nullptr;
     int H = 0, L = 0, num_sms = 148, stft_per_warp = 0;   // 0: derive from the stream count
     int parity = 0;   // h[parity] holds h(t-1)
+    int tcap = 1;     // frames per chunk of the bf16 path (slots of feat / spec / mask)
+    int e_ring = 1;   // slots of the encoder output ring
+    int ola_par = 0;  // ola[ola_par] holds the overlap-add state
+    int last_slot = 0;   // scratch slot of the last finished step (debug_read)
     // model
     __nv_bfloat16 *enc_w = nullptr, *dec_w = nullptr, *wih[kMaxLayers] = {}, *whh[kMaxLayers] = {};
     float *enc_b = nullptr, *dec_b = nullptr, *bih[kMaxLayers] = {}, *bhh[kMaxLayers] = {};
     float2 *tables = nullptr;   // lane-major FFT constants
     // state
     int16_t *tail = nullptr;
-    float *ola = nullptr;
+    float *ola[2] = {};          // [Bp][256]; fp32 path: both entries are the same buffer
     float *h[2] = {};            // [L][Bp][H]
     __nv_bfloat16 *hb[2] = {};   // [L][Bp][H]   (bf16 path)
     // scratch
-    void *feat = nullptr;        // fp32 | bf16 [Bp][256]
-    float *spec = nullptr;       // [Bp][512]
-    void *e = nullptr;           // fp32 | bf16 [Bp][H]
-    float *mask = nullptr;       // [Bp][256]
+    void *feat = nullptr;        // fp32 | bf16 [tcap][Bp][256]
+    float *spec = nullptr;       // [tcap][Bp][512]
+    void *e = nullptr;           // fp32 | bf16 [e_ring][Bp][H]
+    float *mask = nullptr;       // [tcap][Bp][256]
     // staging for host-buffer calls
     int16_t *d_in[kHostRing] = {}, *d_out[kHostOutRing] = {};   // [B][staging_frames][256] / [B][staging_out_frames][256] each
     size_t staging_frames = 0, staging_out_frames = 0;
@@ -285,36 +292,47 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             }
         }
         KCHECK(upload(p->allocs, &p->tables, tab));
-        KCHECK(dev_alloc(p->allocs, &p->spec, Bp * kNfft));
-        KCHECK(dev_alloc(p->allocs, &p->mask, Bp * kBins));
+        if (precision == kBf16) {
+            // frames per chunk: as many as keep feat + spec + mask under 512 MB, at most 64 (KOALA_CHUNK_FRAMES overrides)
+            const size_t slot_bytes = Bp * (kNfft * 4 + kBins * 4 + kBins * 2);
+            int cap = 64;
+            while (cap > 1 && (size_t) cap * slot_bytes > ((size_t) 512 << 20)) cap >>= 1;
+            if (const char *e = getenv("KOALA_CHUNK_FRAMES")) cap = std::max(1, std::min(256, atoi(e)));
+            p->tcap = cap;
+            p->e_ring = std::min(cap, kFuSlots);
+        }
+        const size_t T = p->tcap;
+        KCHECK(dev_alloc(p->allocs, &p->spec, T * Bp * kNfft));
+        KCHECK(dev_alloc(p->allocs, &p->mask, T * Bp * kBins));
         if (precision == kFp32) {
             KCHECK(dev_alloc(p->allocs, &p->tail, Bp * kFrame));
-            KCHECK(dev_alloc(p->allocs, &p->ola, Bp * kFrame));
+            KCHECK(dev_alloc(p->allocs, &p->ola[0], Bp * kFrame));
+            p->ola[1] = p->ola[0];
             for (int i = 0; i < 2; i++) KCHECK(dev_alloc(p->allocs, &p->h[i], L * Bp * H));
         } else {
             // One arena for everything that survives a step: fp32 h (updated IN PLACE: a GRU tile reads and writes only its own
             // [256 streams x 64 units] slice; the other tiles read the bf16 copies, which stay ping-pong), both bf16 copies,
-            // the overlap-add tail and the analysis tail.  In-place h takes 32 MB off the ~160 MB a step of 8192 streams touches
+            // the overlap-add halves and the analysis tail.  In-place h takes 32 MB off the ~160 MB a step of 8192 streams touches
             // (126 MB L2): 90.4 -> 83.7 us per step.  (A persisting L2 access-policy window over the arena was tried and made
             // the step 44 % SLOWER -- the set-aside starves the per-step scratch -- so the arena uses the normal policy.)
             const size_t h_bytes = L * Bp * H * sizeof(float), hb_bytes = L * Bp * H * sizeof(__nv_bfloat16);
             const size_t ola_bytes = Bp * kFrame * sizeof(float), tail_bytes = Bp * kFrame * sizeof(int16_t);
-            p->arena_bytes = h_bytes + 2 * hb_bytes + ola_bytes + tail_bytes;
+            p->arena_bytes = h_bytes + 2 * hb_bytes + 2 * ola_bytes + tail_bytes;
             KCHECK(dev_alloc(p->allocs, &p->arena, p->arena_bytes));
             uint8_t *a = p->arena;
             p->h[0] = p->h[1] = (float *) a; a += h_bytes;
             for (int i = 0; i < 2; i++) { p->hb[i] = (__nv_bfloat16 *) a; a += hb_bytes; }
-            p->ola = (float *) a; a += ola_bytes;
+            for (int i = 0; i < 2; i++) { p->ola[i] = (float *) a; a += ola_bytes; }
             p->tail = (int16_t *) a;
         }
         if (precision == kFp32) {
             KCHECK(dev_alloc(p->allocs, (float **) &p->feat, Bp * kBins));
             KCHECK(dev_alloc(p->allocs, (float **) &p->e, Bp * H));
         } else {
-            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->feat, Bp * kBins));
-            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->e, Bp * H));
+            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->feat, T * Bp * kBins));
+            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->e, (size_t) p->e_ring * Bp * H));
             TcModel tm;
-            tm.H = (int) H; tm.L = (int) L; tm.Bp = (int) Bp;
+            tm.H = (int) H; tm.L = (int) L; tm.Bp = (int) Bp; tm.tcap = p->tcap; tm.e_ring = p->e_ring;
             tm.enc_w = p->enc_w; tm.dec_w = p->dec_w; tm.enc_b = p->enc_b; tm.dec_b = p->dec_b;
             for (size_t l = 0; l < L; l++) { tm.wih[l] = p->wih[l]; tm.whh[l] = p->whh[l]; tm.bih[l] = p->bih[l]; tm.bhh[l] = p->bhh[l]; }
             tm.feat = (__nv_bfloat16 *) p->feat; tm.e = (__nv_bfloat16 *) p->e; tm.mask = p->mask;
@@ -362,12 +380,23 @@ Engine::~Engine() {
     delete p_;
 }
 
+// STFT launches: warps walk a fixed number of items each; with items / resident warps rounded DOWN the grid is slightly larger
+// than what fits at once (kStftCtasPerSm CTAs of kStftWarps warps per SM) and its CTAs are short, which lets the next
+// kernel of the programmatic-dependent-launch chain move in earlier (8192 streams: 2 per warp, 82.4 vs 83.6 us per step)
+static int stft_grid_for(int items, int num_sms, int per_warp_override) {
+    const int resident_warps = num_sms * kStftCtasPerSm * kStftWarps;
+    const int per_warp = per_warp_override > 0 ? per_warp_override : std::max(1, items / resident_warps);
+    return std::max(1, (items + kStftWarps * per_warp - 1) / (kStftWarps * per_warp));
+}
+
 Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long long stride, void *stream_,
-                              std::vector<std::string> *errors, long long out_stride) {
+                              std::vector<std::string> *errors, long long out_stride, long long frame_stride, long long out_frame_stride) {
     if (out_stride == 0) out_stride = stride;
-    if (!pcm || !out || frames < 0 || stride < kFrame || (stride & 7) || out_stride < kFrame || (out_stride & 7) || ((uintptr_t) pcm & 15) ||
-        ((uintptr_t) out & 15)) {
-        if (errors) errors->push_back("PCM buffers must be non-NULL, 16-byte aligned, with a stream stride >= 256 and a multiple of 8.");
+    if (frame_stride == 0) frame_stride = kFrame;
+    if (out_frame_stride == 0) out_frame_stride = frame_stride;
+    if (!pcm || !out || frames < 0 || stride < kFrame || (stride & 7) || out_stride < kFrame || (out_stride & 7) || frame_stride < kFrame ||
+        (frame_stride & 7) || out_frame_stride < kFrame || (out_frame_stride & 7) || ((uintptr_t) pcm & 15) || ((uintptr_t) out & 15)) {
+        if (errors) errors->push_back("PCM buffers must be non-NULL, 16-byte aligned, with stream and frame strides >= 256 and multiples of 8.");
         return kInvalidArgument;
     }
     Impl *p = p_;
@@ -380,21 +409,16 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     if (p->fu) KCHECK(serialize_fused_launches(device_, p, st, &p->ev_order));
     const int B = n_, Bp = npad_, H = p->H, L = p->L;
     const size_t LBH = (size_t) Bp * H;
-    // STFT kernels: warps walk a fixed number of streams each; with B / resident warps rounded DOWN the grid is slightly larger
-    // than what fits at once (kStftCtasPerSm CTAs of kStftWarps warps per SM) and its CTAs are short, which lets the next
-    // kernel of the programmatic-dependent-launch chain move in earlier (8192 streams: 2 per warp, 82.4 vs 83.6 us per step)
-    const int resident_warps = p->num_sms * kStftCtasPerSm * kStftWarps;
-    const int stft_per_warp = p->stft_per_warp > 0 ? p->stft_per_warp : std::max(1, B / resident_warps);
-    const int stft_grid = std::max(1, (B + kStftWarps * stft_per_warp - 1) / (kStftWarps * stft_per_warp));
     KernelProfiler *prof = p->prof;
     static const bool only_masknet = [] { const char *e = getenv("KOALA_B200_ONLY_MASKNET"); return e && e[0] == '1'; }();
-    for (int t = 0; t < frames; t++) {
-        PcmView v{pcm, out, stride, out_stride, t};
-        const int cur = p->parity, nxt = cur ^ 1;
-        if (precision_ == kFp32) {
-            float *feat = (float *) p->feat, *e = (float *) p->e;
+    if (precision_ == kFp32) {
+        const int grid = stft_grid_for(B, p->num_sms, p->stft_per_warp);
+        float *feat = (float *) p->feat, *e = (float *) p->e;
+        for (int t = 0; t < frames; t++) {
+            PcmView v{pcm, out, stride, out_stride, frame_stride, out_frame_stride, t};
+            const int cur = p->parity, nxt = cur ^ 1;
             if (prof) prof->begin(kKernFrontend, st);
-            launch_pdl(false, frontend_kernel<float>, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->tail, p->spec, feat, p->tables);
+            launch_pdl(false, frontend_kernel<float>, dim3(grid), dim3(kStftWarps * 32), 0, st, v, B, 1, (long long) Bp, p->tail, p->spec, feat, p->tables);
             if (prof) { prof->end(st); prof->begin(kKernEnc, st); }
             launch_pdl(false, linear_fp32_kernel<kActRelu>, dim3(Bp / kF32Bm, H / kF32LinN), dim3(256), 0, st, feat, p->enc_w, p->enc_b, e, kBins, H);
             if (prof) prof->end(st);
@@ -408,28 +432,44 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
             }
             if (prof) prof->begin(kKernDec, st);
             launch_pdl(false, linear_fp32_kernel<kActSigmoid>, dim3(Bp / kF32Bm, kBins / kF32LinN), dim3(256), 0, st, x, p->dec_w, p->dec_b, p->mask, H, kBins);
+            if (prof) { prof->end(st); prof->begin(kKernBackend, st); }
+            launch_pdl(false, backend_kernel, dim3(grid), dim3(kStftWarps * 32), 0, st, v, B, 1, 1, (long long) Bp, p->spec, p->mask, p->ola[0], p->ola[0],
+                                                                            p->tail, p->tables);
             if (prof) prof->end(st);
-            launches_ += 3 + L;
-        } else if (only_masknet) {      // tuning aid (KOALA_B200_ONLY_MASKNET=1): the fused kernel alone, back to back, on stale features
-            if (prof) prof->begin(kKernMasknet, st);
-            launches_ += fu_masknet_step(p->fu, cur, st);
-            if (prof) prof->end(st);
+            launches_ += 4 + L;
             p->parity = nxt;
-            continue;
-        } else {
-            if (prof) prof->begin(kKernFrontend, st);
-            launch_pdl(true, frontend_kernel<__nv_bfloat16>, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->tail, p->spec,
-                                                                                  (__nv_bfloat16 *) p->feat, p->tables);
-            if (prof) prof->end(st);
-            if (prof) prof->begin(kKernMasknet, st);
-            launches_ += 1 + fu_masknet_step(p->fu, cur, st);
-            if (prof) prof->end(st);
         }
-        if (prof) prof->begin(kKernBackend, st);
-        launch_pdl(precision_ == kBf16, backend_kernel, dim3(stft_grid), dim3(kStftWarps * 32), 0, st, v, B, p->spec, p->mask, p->ola, p->tables);
+        KCHECK(cudaGetLastError());
+        return kSuccess;
+    }
+    // bf16 path: chunks of up to tcap frames, three launches per chunk chained with programmatic dependent launch
+    const int resident_warps = p->num_sms * kStftCtasPerSm * kStftWarps;
+    for (int t0 = 0; t0 < frames; t0 += p->tcap) {
+        const int tc = std::min(p->tcap, frames - t0);
+        PcmView v{pcm, out, stride, out_stride, frame_stride, out_frame_stride, t0};
+        if (only_masknet) {      // tuning aid (KOALA_B200_ONLY_MASKNET=1): the fused kernel alone, back to back, on stale features
+            if (prof) prof->begin(kKernMasknet, st);
+            launches_ += fu_masknet_steps(p->fu, p->parity, tc, st);
+            if (prof) prof->end(st);
+            p->parity ^= tc & 1;
+            continue;
+        }
+        if (prof) prof->begin(kKernFrontend, st);
+        launch_pdl(true, frontend_kernel<__nv_bfloat16>, dim3(stft_grid_for(B * tc, p->num_sms, p->stft_per_warp)), dim3(kStftWarps * 32), 0, st, v, B, tc,
+                   (long long) Bp, p->tail, p->spec, (__nv_bfloat16 *) p->feat, p->tables);
+        if (prof) { prof->end(st); prof->begin(kKernMasknet, st); }
+        launches_ += 1 + fu_masknet_steps(p->fu, p->parity, tc, st);
+        if (prof) { prof->end(st); prof->begin(kKernBackend, st); }
+        // synthesis runs: as long as the stream count allows while still filling the GPU about twice over
+        const int runs_wanted = (2 * resident_warps + B - 1) / B;
+        const int run = std::max(1, tc / runs_wanted), runs = (tc + run - 1) / run;
+        launch_pdl(true, backend_kernel, dim3(stft_grid_for(B * runs, p->num_sms, p->stft_per_warp)), dim3(kStftWarps * 32), 0, st, v, B, tc, run,
+                   (long long) Bp, p->spec, p->mask, p->ola[p->ola_par], p->ola[p->ola_par ^ 1], p->tail, p->tables);
         if (prof) prof->end(st);
         launches_ += 1;
-        p->parity = nxt;
+        p->ola_par ^= 1;
+        p->parity ^= tc & 1;
+        p->last_slot = tc - 1;
     }
     KCHECK(cudaGetLastError());
     return kSuccess;
@@ -507,9 +547,8 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
         KCHECK(cudaStreamWaitEvent(p->stream, p->ev_in[ib], 0));
         if (slot == 0 && blk >= kHostOutRing) KCHECK(cudaStreamWaitEvent(p->stream, p->ev_out[ob], 0));
         Status st = kSuccess;
-        if (time_major) {       // staging buffers are [tc][B][256]: one step per frame, streams 256 samples apart
-            for (int t = 0; t < tc && st == kSuccess; t++)
-                st = process_device(p->d_in[ib] + (size_t) t * n_ * kFrame, p->d_out[ob] + (size_t) t * n_ * kFrame, 1, kFrame, p->stream, errors);
+        if (time_major) {       // staging buffers are [tc][B][256]: streams 256 samples apart, frames B * 256
+            st = process_device(p->d_in[ib], p->d_out[ob], tc, kFrame, p->stream, errors, kFrame, (long long) n_ * kFrame, (long long) n_ * kFrame);
         } else {
             st = process_device(p->d_in[ib], p->d_out[ob] + (size_t) slot * Tc * kFrame, tc, (long long) p->staging_frames * kFrame, p->stream,
                                 errors, (long long) p->staging_out_frames * kFrame);
@@ -534,7 +573,7 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
     return kSuccess;
 }
 
-__global__ void reset_streams_kernel(const int32_t *__restrict__ ids, int n_ids, int n_streams, int16_t *tail, float *ola,
+__global__ void reset_streams_kernel(const int32_t *__restrict__ ids, int n_ids, int n_streams, int16_t *tail, float *ola, float *ola1,
                                      float *h0, float *h1, __nv_bfloat16 *hb0, __nv_bfloat16 *hb1, int H, int L, size_t LBH) {
     const int i = blockIdx.x;
     if (i >= n_ids) return;
@@ -543,6 +582,7 @@ __global__ void reset_streams_kernel(const int32_t *__restrict__ ids, int n_ids,
     for (int k = threadIdx.x; k < kFrame; k += blockDim.x) {
         tail[(size_t) s * kFrame + k] = 0;
         ola[(size_t) s * kFrame + k] = 0.0f;
+        ola1[(size_t) s * kFrame + k] = 0.0f;
     }
     for (int l = 0; l < L; l++)
         for (int k = threadIdx.x; k < H; k += blockDim.x) {
@@ -566,8 +606,8 @@ Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> 
     p->has_last = true;
     if (!stream_ids) {
         KCHECK(cudaMemsetAsync(p->tail, 0, Bp * kFrame * sizeof(int16_t), p->stream));
-        KCHECK(cudaMemsetAsync(p->ola, 0, Bp * kFrame * sizeof(float), p->stream));
         for (int i = 0; i < 2; i++) {
+            KCHECK(cudaMemsetAsync(p->ola[i], 0, Bp * kFrame * sizeof(float), p->stream));
             KCHECK(cudaMemsetAsync(p->h[i], 0, L * Bp * H * sizeof(float), p->stream));
             if (p->hb[i]) KCHECK(cudaMemsetAsync(p->hb[i], 0, L * Bp * H * sizeof(__nv_bfloat16), p->stream));
         }
@@ -585,7 +625,7 @@ Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> 
             int32_t *d_ids = nullptr;
             KCHECK(cudaMalloc((void **) &d_ids, n * sizeof(int32_t)));
             cudaError_t e1 = cudaMemcpyAsync(d_ids, stream_ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream);
-            reset_streams_kernel<<<n, 128, 0, p->stream>>>(d_ids, n, n_, p->tail, p->ola, p->h[0], p->h[1], p->hb[0], p->hb[1],
+            reset_streams_kernel<<<n, 128, 0, p->stream>>>(d_ids, n, n_, p->tail, p->ola[0], p->ola[1], p->h[0], p->h[1], p->hb[0], p->hb[1],
                                                           (int) H, (int) L, Bp * H);
             cudaError_t e2 = cudaStreamSynchronize(p->stream);
             cudaFree(d_ids);
@@ -622,6 +662,7 @@ Status Engine::profile_read(double *ms, long long *count, int n_classes, std::ve
 }
 
 void *Engine::own_stream() const { return p_->stream; }
+int Engine::chunk_frames() const { return p_->tcap; }
 
 Status Engine::synchronize(std::vector<std::string> *errors) {
     KCHECK(cudaSetDevice(device_));
@@ -638,11 +679,14 @@ Status Engine::debug_read(const char *name, void *dst, size_t bytes, std::vector
     size_t avail = 0;
     const size_t esz = precision_ == kFp32 ? 4 : 2;
     const std::string nm(name ? name : "");
-    if (nm == "feat") { src = p->feat; avail = B * kBins * esz; }
-    else if (nm == "spec") { src = p->spec; avail = B * kNfft * 4; }
-    else if (nm == "mask") { src = p->mask; avail = B * kBins * 4; }
-    else if (nm == "e") { src = p->e; avail = B * H * esz; }
-    else if (nm == "ola") { src = p->ola; avail = B * kFrame * 4; }
+    // scratch of the last finished step: slot last_slot of the chunk buffers, ring slot (steps so far) % ring of e
+    const size_t slot = precision_ == kBf16 ? (size_t) p->last_slot : 0;
+    const size_t e_slot = (p->fu && p->fu->epoch > 0) ? (size_t) ((p->fu->epoch - 1) % p->e_ring) : 0;
+    if (nm == "feat") { src = (const uint8_t *) p->feat + slot * Bp * kBins * esz; avail = B * kBins * esz; }
+    else if (nm == "spec") { src = p->spec + slot * Bp * kNfft; avail = B * kNfft * 4; }
+    else if (nm == "mask") { src = p->mask + slot * Bp * kBins; avail = B * kBins * 4; }
+    else if (nm == "e") { src = (const uint8_t *) p->e + e_slot * Bp * H * esz; avail = B * H * esz; }
+    else if (nm == "ola") { src = p->ola[p->ola_par]; avail = B * kFrame * 4; }
     else if (nm == "tail") { src = p->tail; avail = B * kFrame * 2; }
     else if (nm == "trace" && p->fu && p->fu->trace) { src = p->fu->trace; avail = 2048 * sizeof(long long); }
     else if (nm.size() == 2 && nm[0] == 'h' && nm[1] >= '0' && nm[1] < '0' + p->L) {

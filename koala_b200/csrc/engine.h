@@ -38,11 +38,15 @@ public:
     int device() const { return device_; }
     int precision() const { return precision_; }
 
-    // pcm / out: frame t of stream s at base + s * stride + t * 256 (int16 samples).  Device pointers, 16-byte aligned,
-    // stride a multiple of 8.  Enqueues `frames` consecutive steps on `stream` (a cudaStream_t taken literally: nullptr is
-    // the legacy default stream; own_stream() is the engine's private one) and returns without synchronising.
+    // pcm / out: frame t of stream s at base + s * stride + t * frame_stride (int16 samples; frame_stride 256 for stream-major
+    // buffers, streams * 256 with stride 256 for time-major ones).  Device pointers, 16-byte aligned, strides multiples of 8.
+    // Enqueues `frames` consecutive steps on `stream` (a cudaStream_t taken literally: nullptr is the legacy default stream;
+    // own_stream() is the engine's private one) and returns without synchronising.  The bf16 path takes the frames in chunks of
+    // up to chunk_frames(): analysis of the chunk, ONE fused mask-estimator launch walking its steps, synthesis of the chunk.
     Status process_device(const int16_t *pcm, int16_t *out, int frames, long long stride, void *stream,
-                          std::vector<std::string> *errors, long long out_stride = 0 /* 0: same as stride */);
+                          std::vector<std::string> *errors, long long out_stride = 0 /* 0: same as stride */,
+                          long long frame_stride = 0 /* 0: 256 */, long long out_frame_stride = 0 /* 0: same as frame_stride */);
+    int chunk_frames() const;
     // Host buffers, [B][frames][256] or (time_major) [frames][B][256]: H2D copies, steps and D2H copies overlapped, synchronise.
     Status process_host(const int16_t *pcm, int16_t *out, int frames, std::vector<std::string> *errors, bool time_major = false);
     Status reset(const int32_t *stream_ids, int n, std::vector<std::string> *errors);   // ids == nullptr: all streams

@@ -358,10 +358,9 @@ static pv_status_t batch_process(pv_koala_batch_t *object, const int16_t *pcm, i
     std::vector<std::string> errs;
     Status st = koala::kSuccess;
     if (kin == 1) {
-        if (time_major) {   // [num_frames][num_streams][256]: one step per frame, streams 256 samples apart
-            const size_t frame = (size_t) object->engine->num_streams() * koala::kFrame;
-            for (int32_t t = 0; t < num_frames && st == koala::kSuccess; t++)
-                st = object->engine->process_device(pcm + t * frame, enhanced_pcm + t * frame, 1, koala::kFrame, object->engine->own_stream(), &errs);
+        if (time_major) {   // [num_frames][num_streams][256]: streams 256 samples apart, frames num_streams * 256
+            const long long frame = (long long) object->engine->num_streams() * koala::kFrame;
+            st = object->engine->process_device(pcm, enhanced_pcm, num_frames, koala::kFrame, object->engine->own_stream(), &errs, koala::kFrame, frame, frame);
         } else {
             st = object->engine->process_device(pcm, enhanced_pcm, num_frames, (long long) num_frames * koala::kFrame,
                                                 object->engine->own_stream(), &errs);
@@ -390,6 +389,24 @@ PV_API pv_status_t pv_koala_batch_process_async(pv_koala_batch_t *object, const 
     std::vector<std::string> errs;
     Status st = object->engine->process_device(pcm, enhanced_pcm, num_frames, stream_stride, cuda_stream, &errs);
     if (st != koala::kSuccess) return fail_engine(st, errs);
+    return PV_STATUS_SUCCESS;
+}
+
+PV_API pv_status_t pv_koala_batch_process_async_strided(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,
+                                                        int32_t num_frames, int64_t stream_stride, int64_t frame_stride, void *cuda_stream) {
+    if (!object) return fail_null("object");
+    if (!pcm) return fail_null("pcm");
+    if (!enhanced_pcm) return fail_null("enhanced_pcm");
+    std::vector<std::string> errs;
+    Status st = object->engine->process_device(pcm, enhanced_pcm, num_frames, stream_stride, cuda_stream, &errs, stream_stride, frame_stride, frame_stride);
+    if (st != koala::kSuccess) return fail_engine(st, errs);
+    return PV_STATUS_SUCCESS;
+}
+
+PV_API pv_status_t pv_koala_batch_chunk_frames(const pv_koala_batch_t *object, int32_t *chunk_frames) {
+    if (!object) return fail_null("object");
+    if (!chunk_frames) return fail_null("chunk_frames");
+    *chunk_frames = object->engine->chunk_frames();
     return PV_STATUS_SUCCESS;
 }
 

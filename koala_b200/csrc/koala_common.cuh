@@ -70,13 +70,16 @@ struct KernelProfiler {
     }
 };
 
-// Where one step's PCM lives: frame t of stream s starts at in + s * stride + t * 256 and out + s * out_stride + t * 256 (samples).
+// Where a launch's PCM lives: frame t of stream s starts at in + s * stride + t * frame_stride and
+// out + s * out_stride + t * out_frame_stride (samples).  Stream-major buffers: frame stride 256; time-major: stride 256,
+// frame stride = streams * 256.
 struct PcmView {
     const int16_t *in;
     int16_t *out;
     long long stride;       // samples between consecutive streams of `in`
     long long out_stride;   // ... of `out` (differs only inside the host ingest path, whose output blocks are wider)
-    int t;              // frame index inside the caller's buffer
+    long long frame_stride, out_frame_stride;   // samples between consecutive frames of one stream
+    int t;                  // index of the launch's first frame inside the caller's buffer
 };
 
 // ---------------------------------------------------------------------------------------------------------------

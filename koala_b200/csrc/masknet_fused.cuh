@@ -1,35 +1,47 @@
-// koala_b200 -- mask estimator, tensor-core path: ONE persistent kernel per step for encoder -> GRU layers -> decoder.
+// koala_b200 -- mask estimator, tensor-core path: ONE persistent kernel per CHUNK of steps (encoder -> GRU layers -> decoder,
+// for every frame of the chunk).
 //
 // Middle stage of `pv_koala_process` (/root/reference/include/pv_koala.h:65-80), batched over the stream dimension
-// (BASELINE.json configs[2..4]).  The building blocks are those of tcgen05_common.cuh (bf16 operands staged by TMA into
-// 128B-swizzled shared memory, tcgen05.mma.cta_group::2 accumulating fp32 in TMEM, gate math fused into the epilogue);
-// this file is the schedule.  Launching the four GEMM stages as separate kernels cost, per launch, ~10 k cycles before the
-// first MMA (dependent-launch wait, cold operand pipeline) and ~7 k cycles after the last one (final epilogue): a third of
-// a GRU launch and most of an encoder / decoder launch (profiles/r01_step_summary.md).  Here every stage is a SEGMENT of
-// one global list of pair tiles
-//     [encoder tiles | GRU layer 0 tiles | ... | GRU layer L-1 tiles | decoder tiles],  each segment ordered m-major,
-// walked round-robin by persistent CTA pairs (2-CTA clusters on all 148 SMs).  A tile of segment s + 1 needs the rows of its
-// m tile from ALL n tiles of segment s: every CTA bumps a per-(segment, m tile) counter in global memory once its output
-// stores have completed, and the activation producers of a dependent tile test that counter before the first load that
-// needs it.  Tiles are taken in list order, so a tile only ever waits for tiles that started earlier: no deadlock as long
-// as the grid is co-resident (it is sized by cudaOccupancyMaxActiveClusters).  Counters are never reset: launch number
-// `epoch` waits for epoch * (increments per step).  GRU tiles run their h(t-1) part first -- it depends on nothing inside
-// the launch -- so the wait only ever holds the second half of a k loop.
+// (BASELINE.json configs[2..4]) and, inside one launch, walked over TIME: the caller's frame loop
+// (/root/reference/demo/c/koala_demo_file.c:466-521) is strictly serial per stream, so a launch per frame pays the launch head
+// (dependent-launch wait, cold operand pipeline, encoder tiles before the first GRU tile: ~20 k cycles) and tail (store drain:
+// ~8 k) on every frame, and at small stream counts is nothing but dependency latency (profiles/r01_step_summary.md).  Here a
+// launch takes `steps` consecutive frames.  The building blocks are those of tcgen05_common.cuh (bf16 operands staged by TMA
+// into 128B-swizzled shared memory, tcgen05.mma.cta_group::2 accumulating fp32 in TMEM, gate math fused into the epilogue);
+// this file is the schedule: one global list of pair tiles
+//     step 0: [encoder | GRU layer 0 | ... | GRU layer L-1 | decoder],  step 1: [...],  ...      each segment m-major,
+// walked round-robin by persistent CTA pairs (2-CTA clusters on all 148 SMs).  Dependencies are per (segment, 256-stream m
+// tile, step slot) COUNTERS in global memory that are never reset: every CTA of a tile of global step g (steps since the
+// engine was created, 0-based) adds 1 to slot g % 4 of its row once the tile's output stores have completed, so "segment s
+// has finished step g for m tile m" reads counter[s][m][g % 4] >= (g / 4 + 1) * (CTAs per m tile of that segment).  (One
+// counter per row would not do: encoder and decoder tiles of step g + 1 do not depend on those of step g and may finish
+// first; the (w) waits below bound that run-ahead to 3 steps, hence 4 slots.)  A tile of step g and segment s waits for
+//   (x)  segment s-1, step g        the rows of its m tile from every n tile of the previous segment, same step;
+//   (h)  segment s,   step g-1      GRU: every n tile of its own layer's previous step (bf16 h(t-1) operand, fp32 h(t-1) slice);
+//   (w)  before its first store: the readers of what it overwrites -- the encoder output ring slot (GRU layer 0 of step
+//        g - ring), the bf16 state copy of parity g (next segment of step g-2).
+// All waits are for tiles EARLIER in the list and every role of a CTA takes its tiles in list order, so nothing can deadlock
+// as long as the grid is co-resident (it is sized by cudaOccupancyMaxActiveClusters; engine.cu serialises fused launches of
+// different engines).  Waits are relaxed polls of an L2-resident word: the producer's stores are complete in L2 before its
+// release-add, and the consumers read through TMA (L2), so no acquire / proxy fence is needed on the consumer side -- those
+// cost ~2 k cycles in a thread with TMA loads in flight (measured), which would sit on the recurrence's critical path.
+// A GRU tile's k loop has two parts (x: input from the previous segment, h: recurrent); which one runs first is a per-engine
+// choice: big batches run h first (at a launch's first step the encoder rows are still being produced), small batches -- whose
+// throughput is the latency of the chain GRU_l(t-1) -> GRU_l(t) -- run x first, so that only half a k loop follows the wait.
 //
-// Warp roles (23 warps, 736 threads, 80 registers): 0,1 activation (A) producers for even / odd k-blocks, 2 TMEM allocator
-// + MMA issuer (pair leader only), 3,4 weight (B) producers (they do not wait for the previous kernel: weights are
-// constants), 5..20 epilogue (4 per TMEM lane quarter), 21 GRU state warp, 22 linear-tile store warp.
+// Warp roles (23 warps, 736 threads): 0,1 activation (A) producers for even / odd k-blocks, 2 TMEM allocator + MMA issuer
+// (pair leader only), 3,4 weight (B) producers (they never wait: weights are constants), 5..20 epilogue (4 per TMEM lane
+// quarter), 21 GRU state warp, 22 linear-tile store warp.
 //   GRU epilogue: two PASSES of 32 units through two staging buffers; the state warp TMA-stores a finished pass (fp32 h(t)
-//   in place of h(t-1), plus its bf16 copy) and requests the fp32 h(t-1) box of the pass two ahead into the drained buffer.
+//   in place of h(t-1), plus its bf16 copy) and requests the fp32 h(t-1) box of the pass two ahead into the drained buffer
+//   (only if that tile's (h) dependency already holds: it must never block while passes of its own pair are unstored).
 //   Linear epilogue: the accumulator is handed back after four TMEM loads; outputs are staged in a separate 32 KB region
-//   (encoder: the CTA's whole [128][128] bf16 tile; decoder: [128][128] fp32, half of it in the by then idle GRU boxes) and
-//   TMA-stored by warp 22.
+//   (encoder: the CTA's whole [128][128] bf16 tile; decoder: two rounds of [128][64] fp32) and TMA-stored by warp 22.
 // Shared memory: 5 operand stages x 28 KB + 48 KB GRU staging + 32 KB linear staging + barriers / biases = 223 KB.
 //
-// What bounds it (8192 streams, B200; profiles/r01_step_summary.md): operand delivery.  Skipping every tcgen05.mma leaves
-// the kernel time unchanged (66.5 vs 65.9 us); the SMs ingest ~28 KB per k-block per ~500 cycles each (8.3 KB/clk over the
-// chip), and a GRU tile with N = 192 needs 73 B/clk/SM at full MMA rate.  TMEM (4 accumulator columns per unit, two
-// buffers) caps the tile width, hence the operand bytes per flop.
+// What bounds a GRU tile (8192 streams, B200; profiles/r01_step_summary.md): operand delivery -- the SMs ingest ~28 KB per
+// k-block per ~500 cycles each, and a tile with N = 192 would need 73 B/clk/SM at full MMA rate.  TMEM (4 accumulator columns
+// per unit, two buffers) caps the tile width, hence the operand bytes per flop.
 #pragma once
 
 #include <string.h>
@@ -46,48 +58,41 @@ namespace koala {
 #endif
 constexpr int kFuStages = KOALA_FU_STAGES;
 constexpr int kFuStageBytes = kTcABytes + (kGruRows / 2) * 128;   // 28 KB: A [128][64] + B up to [96][64] bf16 (linear tiles: 64 rows)
-#ifndef KOALA_FU_PN
-#define KOALA_FU_PN 1
-#endif
-constexpr int kFuPN = KOALA_FU_PN;                                // CTA pairs per cluster; 2 = neighbouring n tiles of one m tile with activation multicast
-                                                                  // (33 clusters = 132 SMs, measured 2 % slower than 74 plain pairs)
-constexpr int kFuCluster = 2 * kFuPN;
-constexpr int kFuARows = kTcBlockM / kFuPN;                       // rows of A each CTA fetches and multicasts
+constexpr int kFuCluster = 2;                                     // one CTA pair per cluster (4-CTA clusters with activation multicast: 2 % slower, r01)
 constexpr int kFuLinN = 128;                                      // outputs per linear pair tile
 constexpr int kFuBoxF32 = kTcBlockM * 32 * 4;                     // staging box [128 rows][32 fp32], 128B-swizzled
 constexpr int kFuBoxB16 = kTcBlockM * 32 * 2;                     // staging box [128 rows][32 bf16], plain
-constexpr int kFuLinBytes = 2 * kFuBoxF32;                        // linear tiles: [128][128] bf16 (encoder) or half of [128][128] fp32 (decoder; other half: the GRU boxes)
+constexpr int kFuLinBytes = 2 * kFuBoxF32;                        // linear tiles: [128][128] bf16 (encoder) or one round of [128][64] fp32 (decoder)
 constexpr int kFuLinWarp = kTcStateWarp + 1;                      // stores the linear tiles' staged outputs
 constexpr int kFuThreads = 32 * (kFuLinWarp + 1);                 // 2 + 1 + 2 + 16 + 1 + 1 warps
 constexpr int kFuSmemBytes = kFuStages * kFuStageBytes + 2 * (kFuBoxF32 + kFuBoxB16) + kFuLinBytes + kTcTailBytes;
 constexpr int kFuMaxSegs = kMaxLayers + 2;
 constexpr int kFuArrivals = kTcEpiWarps;                          // epilogue barriers: one arrival per warp (after __syncwarp), not per thread
+constexpr int kFuSlots = 4;                                       // step slots per dependency counter row (>= encoder ring, >= 3)
 enum FuMap : int { kMapA0 = 0, kMapA1, kMapB0, kMapB1, kMapHp, kMapHn, kMapHb, kFuMapsPerSeg };
 
 struct FuSeg {
     int mode;                 // kTcEnc | kTcGru | kTcDec
-    int n_ctiles;             // cluster tiles along n (= pair tiles / kFuPN)
-    int kb_per_part, parts;   // k-blocks of 64 per operand part; GRU has two parts (run as h(t-1) first, then x)
-    int tile_begin;           // index of the segment's first tile in the global list
-    int dep, done;            // counter rows this segment waits on / bumps (-1: none)
-    unsigned dep_per_step;    // increments per m tile and step of the row it waits on (CTAs that write those rows)
+    int n_tiles;              // pair tiles along n
+    int kb_per_part, parts;   // k-blocks of 64 per operand part; GRU has two parts (x and h)
+    int tile_begin;           // index of the segment's first tile inside one step's list
+    int x_first;              // GRU: the x part runs before the h part
+    unsigned inc;             // what one step adds to this segment's counter of an m tile (2 CTAs per n tile)
     const float *bias0, *bias1;
-    const __nv_bfloat16 *a1;  // GRU: bf16 h(t-1) operand [Bp][H], for the L2 prefetch of the next tile
+    const __nv_bfloat16 *a1[2];   // GRU: bf16 h(t-1) operand [Bp][H] by state parity, for the L2 prefetch of the next tile
 };
 struct FuArgs {
-    int nseg, num_m_tiles, total_tiles, H;
-    unsigned epoch;
-    unsigned *counters;       // [nseg][num_m_tiles]
-    const CUtensorMap *maps;  // [nseg][kFuMapsPerSeg], global memory
+    int nseg, num_m_tiles, tiles_per_step, total_tiles, H, Bp;
+    int steps;                // frames in this launch
+    int cur0;                 // parity of the state buffers that hold h(t-1) of the launch's first step
+    int e_ring;               // slots of the encoder-output ring (slot = global step % e_ring), <= kFuSlots
+    long long epoch0;         // steps completed before this launch = global index of the launch's first step
+    unsigned *counters;       // [nseg][num_m_tiles][kFuSlots]
+    const CUtensorMap *maps;  // [2 parities][nseg][kFuMapsPerSeg], global memory
     long long *trace;
     FuSeg seg[kFuMaxSegs];
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -96,18 +101,73 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
 __device__ __forceinline__ void red_release_gpu(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void bulk_wait_read_but1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// blocks until the counter has reached `target` (modular comparison: the counters wrap)
+__device__ __forceinline__ void fu_wait_counter(const unsigned *ctr, unsigned target) {
+    while ((int) (ld_relaxed_gpu(ctr) - target) < 0) {
+    }
+}
 
-// position of one cluster in the global tile list
+// position of one pair tile in the global list
 struct FuTile {
-    int s, m, n0;             // segment, m tile, first n tile of the cluster tile
+    int t, s, m, n;           // step inside the launch, segment, m tile, n tile
+    int par;                  // parity of the state buffers that hold h(t-1) of this step
+    long long g;              // global step index (0-based): epoch0 + t
 };
 __device__ __forceinline__ FuTile fu_decode(const FuArgs &a, int g) {
+    FuTile r;
+    r.t = g / a.tiles_per_step;
+    const int local = g - r.t * a.tiles_per_step;
     int s = 0;
-    while (s + 1 < a.nseg && g >= a.seg[s + 1].tile_begin) ++s;
-    const int local = g - a.seg[s].tile_begin, nc = a.seg[s].n_ctiles;
-    return FuTile{s, local / nc, (local % nc) * kFuPN};
+    while (s + 1 < a.nseg && local >= a.seg[s + 1].tile_begin) ++s;
+    const int in_seg = local - a.seg[s].tile_begin, nt = a.seg[s].n_tiles;
+    r.s = s;
+    r.m = in_seg / nt;
+    r.n = in_seg - r.m * nt;
+    r.par = (a.cur0 + r.t) & 1;
+    r.g = a.epoch0 + r.t;
+    return r;
+}
+// "segment s has finished global step g for m tile m": the counter and the value it has reached by then.  False: nothing to
+// wait for (before the engine's first step).
+__device__ __forceinline__ bool fu_done_ctr(const FuArgs &a, int s, int m, long long g, const unsigned *&ctr, unsigned &target) {
+    if (g < 0) return false;
+    ctr = a.counters + ((size_t) s * a.num_m_tiles + m) * kFuSlots + (int) (g % kFuSlots);
+    target = (unsigned) (g / kFuSlots + 1) * a.seg[s].inc;
+    return true;
+}
+__device__ __forceinline__ void fu_signal_done(const FuArgs &a, const FuTile &t) {
+    red_release_gpu(a.counters + ((size_t) t.s * a.num_m_tiles + t.m) * kFuSlots + (int) (t.g % kFuSlots), 1u);
+}
+// the two dependencies of a tile's loads: (x) previous segment, same step; (h) own segment, previous step
+__device__ __forceinline__ bool fu_dep_x(const FuArgs &a, const FuTile &t, const unsigned *&ctr, unsigned &target) {
+    return t.s > 0 && fu_done_ctr(a, t.s - 1, t.m, t.g, ctr, target);
+}
+__device__ __forceinline__ bool fu_dep_h(const FuArgs &a, const FuTile &t, const unsigned *&ctr, unsigned &target) {
+    return a.seg[t.s].mode == kTcGru && fu_done_ctr(a, t.s, t.m, t.g - 1, ctr, target);
+}
+// (w): the readers of the buffer this tile's stores overwrite must be done
+__device__ __forceinline__ void fu_wait_war(const FuArgs &a, const FuTile &t) {
+    const FuSeg &sg = a.seg[t.s];
+    const unsigned *ctr = nullptr;
+    unsigned target = 0;
+    bool need = false;
+    if (sg.mode == kTcEnc)         // ring slot g % ring was read by GRU layer 0 of step g - ring
+        need = fu_done_ctr(a, 1, t.m, t.g - a.e_ring, ctr, target);
+    else if (sg.mode == kTcGru)    // the bf16 copy this step writes held h(g-2), read as the x operand by the next segment at step g-2
+        need = fu_done_ctr(a, t.s + 1, t.m, t.g - 2, ctr, target);
+    if (need) fu_wait_counter(ctr, target);
 }
 
 __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads, 1) tc_fused_kernel(const __grid_constant__ FuArgs args) {
@@ -122,46 +182,47 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
     uint64_t *full_bar = bars, *empty_bar = bars + kStages;
     uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
-    uint64_t *box_ready = bars + 2 * kStages + 4;        // [2]: staging buffer is free (linear) / holds h(t-1) (GRU)
+    uint64_t *box_ready = bars + 2 * kStages + 4;        // [2]: the staging buffer holds h(t-1) of a pass
     uint64_t *staged = bars + 2 * kStages + 6;           // [2]: the epilogue has staged a pass in the buffer
-    uint64_t *lin_free = bars + 2 * kStages + 8, *lin_staged = bars + 2 * kStages + 9;
-    uint64_t *gru_done = bars + 2 * kStages + 10;         // the state warp has drained: the GRU staging boxes are free for good
+    uint64_t *lin_free = bars + 2 * kStages + 8;         // the stores of a linear round have read the staging region
+    uint64_t *lin_staged16 = bars + 2 * kStages + 9;     // encoder tile staged (all 16 epilogue warps)
+    uint64_t *lin_staged8 = bars + 2 * kStages + 10;     // one decoder round staged (the 8 warps that own its columns)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 11);
     float *s_bias = reinterpret_cast<float *>(tail + 256);   // [2 accumulator buffers][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t crank = cluster_ctarank();      // rank in the cluster = 2 * pair + position in pair
-    const uint32_t rank = crank & 1;               // 0 = pair leader (issues the MMAs), 1 = peer
-    const uint32_t leader = crank & ~1u;           // cluster rank of my pair's leader
-    const int qn = (int) (crank >> 1);             // my pair's n tile inside the cluster tile
-    const uint16_t pair_mask = (uint16_t) (3u << leader), all_mask = (uint16_t) ((1u << kFuCluster) - 1);
+    const uint32_t rank = cluster_ctarank();       // 0 = pair leader (issues the MMAs), 1 = peer
+    constexpr uint32_t leader = 0;
+    constexpr uint16_t pair_mask = 3;
     [[maybe_unused]] long long *trace = (args.trace != nullptr && blockIdx.x < 2) ? args.trace + blockIdx.x * 1024 : nullptr;
 #ifdef KOALA_FU_TRACE      // clock64 timeline of cluster 0 (tools/gpu_trace.py builds this variant); compiled out of the product
-#define KTRACE(slot) do { if (trace && (slot) < 1024) trace[(slot)] = clock64(); } while (0)
+#define KTRACE(slot) do { if (trace && (slot) < 1020) trace[(slot)] = clock64(); } while (0)
+#define KTRACE_HDR(slot) do { if (trace) trace[(slot)] = clock64(); } while (0)
 #else
 #define KTRACE(slot) do { } while (0)
+#define KTRACE_HDR(slot) do { } while (0)
 #endif
-    if (threadIdx.x == 0) KTRACE(1020);
+    if (threadIdx.x == 0) KTRACE_HDR(1020);
     pdl_launch_dependents();
     const int cluster_id = blockIdx.x / kFuCluster, num_clusters = gridDim.x / kFuCluster;
     const int total = args.total_tiles;
 
     if (warp == 0) {
-        for (int i = lane; i < args.nseg * kFuMapsPerSeg; i += 32) prefetch_tmap(args.maps + i);
+        for (int i = lane; i < 2 * args.nseg * kFuMapsPerSeg; i += 32) prefetch_tmap(args.maps + i);
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) {
                 mbar_init(&full_bar[s], 1);          // leader's copy is the one in use: 1 arrive.expect_tx + 2 CTAs' TMA bytes
-                mbar_init(&empty_bar[s], kFuPN);     // one multicast tcgen05.commit from every pair leader of the cluster
+                mbar_init(&empty_bar[s], 1);         // one multicast tcgen05.commit from the pair leader
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&tmem_full[b], 1);         // one multicast tcgen05.commit
-                mbar_init(&tmem_empty[b], 2 * kFuArrivals);     // leader's copy: the epilogue warps (threads) of both CTAs
+                mbar_init(&tmem_empty[b], 2 * kFuArrivals);     // leader's copy: the epilogue warps of both CTAs
                 mbar_init(&box_ready[b], 1);
                 mbar_init(&staged[b], kFuArrivals);
             }
             mbar_init(lin_free, 1);
-            mbar_init(gru_done, 1);
-            mbar_init(lin_staged, kFuArrivals);
+            mbar_init(lin_staged16, kFuArrivals);
+            mbar_init(lin_staged8, kFuArrivals / 2);
             fence_mbar_init();
         }
     }
@@ -170,92 +231,78 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) KTRACE(1021);
+    if (threadIdx.x == 0) KTRACE_HDR(1021);
 
     if (warp == 0 || warp == 1 || warp == 3 || warp == 4) {
         // ===================================================== TMA producers (both CTAs of every pair).  One warp can issue a
         // tensor load only every ~210-380 cycles (tools/micro/tma_rate.cu), so the loads are spread over four warps: warps
         // 0/1 fetch the activation (A) tiles of the even/odd k-blocks, warps 3/4 the weight (B) tiles.  Everything stays
-        // warp-uniform (elect_one) so descriptors live in uniform registers.  Weights do not depend on the previous kernel:
-        // the B producers fill the pipeline while that kernel is still running, only the A producers wait for it.
+        // warp-uniform (elect_one) so descriptors live in uniform registers.  Weights do not depend on anything: the B
+        // producers run ahead (also into the previous kernel's tail); only the A producers wait, for the previous kernel
+        // once and for the dependency counters before the first load of each operand part.
         const bool is_a = warp < 2;
         const int par = is_a ? warp : warp - 3;             // my k-block parity
         if (is_a) pdl_wait();
-        int stage = par, phase = 0;                         // kStages is even: a warp stays on the stages of its parity
-        uint16_t mask_a = 0;                                 // same position in every pair of the cluster
-#pragma unroll
-        for (int j = 0; j < kFuPN; ++j) mask_a |= (uint16_t) (1u << (2 * j + rank));
-        auto arow_of = [&](int m) { return m * kTcPairM + (int) rank * kTcBlockM + qn * kFuARows; };   // first of the 64 rows I fetch
+        int stage = par, phase = 0;                         // kStages is odd or even: see the advance at the bottom of the loop
+        const int arow = (int) rank * kTcBlockM;            // my 128 rows inside the pair's 256-stream tile
         int pit = 0;
-        unsigned seen = 0, seen_this = 0;   // the next tile's dependency counter, sampled one tile early
-        bool seen_valid = false, seen_valid_this = false;
+        unsigned seen_x = 0, seen_h = 0;    // the next tile's dependency counters, sampled one tile early (hides the L2 round trip)
+        bool have_seen = false;
         for (int g = cluster_id; g < total; g += num_clusters, ++pit) {
             const FuTile t = fu_decode(args, g);
             const FuSeg &sg = args.seg[t.s];
-            const CUtensorMap *maps = args.maps + t.s * kFuMapsPerSeg;
+            const CUtensorMap *maps = args.maps + (size_t) (t.par * args.nseg + t.s) * kFuMapsPerSeg;
             const bool gru = sg.mode == kTcGru;
-            const int num_kb = sg.kb_per_part * sg.parts, n = t.n0 + qn;
+            const int kbp = sg.kb_per_part, num_kb = kbp * sg.parts;
             const int brows = gru ? kGruRows / 2 : kFuLinN / 2;         // weight rows each CTA of the pair holds
             const uint32_t pair_tx = 2u * (uint32_t) (kTcABytes + brows * 128);
+            const int hpart = gru ? (sg.x_first ? 1 : 0) : -1;          // position of the h part in the k loop
+            // x operand rows: features of slot t (encoder), encoder-output ring slot (GRU layer 0), else a state copy
+            const int a0_row = t.m * kTcPairM + arow +
+                               (sg.mode == kTcEnc ? t.t * args.Bp : t.s == 1 ? (int) (t.g % args.e_ring) * args.Bp : 0);
+            const int a1_row = t.m * kTcPairM + arow;
+            const unsigned my_seen_x = seen_x, my_seen_h = seen_h;
+            const bool my_have = have_seen;
+            have_seen = false;
             if (warp == 0 && lane == 0) KTRACE(pit * 48 + 0);
-            bool dep_pending = is_a && sg.dep >= 0;
-            seen_valid_this = seen_valid; seen_this = seen;
-            seen_valid = false;
             for (int kb = par; kb < num_kb; kb += 2) {
-                // GRU tiles take their h(t-1) part FIRST: it does not depend on the previous segment, so the dependency wait
-                // below only holds the second half of the k loop and is usually over by the time it is reached
-                const bool second = gru && kb < sg.kb_per_part;      // second operand pair (A1 / B1) = the h part
-                if (dep_pending && !second) {
-                    // the rows of my m tile are written by every n tile of the previous segment: wait until all those CTAs have
-                    // signalled (their stores completed before the release).  The counter was already sampled during the
-                    // previous tile, so in the steady state nothing is waited for here.  The fast path is a relaxed
-                    // L1-bypassing load: the TMA unit reads through L2, where the signalled rows already are, and an acquire
-                    // or a proxy fence in this thread waits for its own outstanding TMA loads (~2 k cycles per tile, measured).
-                    const unsigned target = args.epoch * sg.dep_per_step;
-                    if (!seen_valid_this || (int) (seen_this - target) < 0) {
-                        const unsigned *ctr = args.counters + (size_t) sg.dep * args.num_m_tiles + t.m;
-                        while ((int) (ld_acquire_gpu(ctr) - target) < 0) __nanosleep(40);
-                        fence_proxy_async_all();
-                    }
-                    dep_pending = false;
-                    if (warp == 0 && lane == 0) KTRACE(pit * 48 + 12);
+                const int part = kb >= kbp ? 1 : 0;
+                const bool hp = part == hpart;
+                if (is_a && (kb == par || kb == kbp + par)) {           // my first load of this operand part: its producers must be done
+                    const unsigned *ctr = nullptr;
+                    unsigned target = 0;
+                    const bool need = hp ? fu_dep_h(args, t, ctr, target) : fu_dep_x(args, t, ctr, target);
+                    if (need && !(my_have && (int) ((hp ? my_seen_h : my_seen_x) - target) >= 0)) fu_wait_counter(ctr, target);
+                    if (warp == 0 && lane == 0) KTRACE(pit * 48 + 12 + part);
                 }
-                mbar_wait(&empty_bar[stage], phase ^ 1);     // slot free in every CTA of the cluster
+                mbar_wait(&empty_bar[stage], phase ^ 1);     // slot free in both CTAs of the pair
                 if (is_a && lane == 0) KTRACE(pit * 48 + 16 + kb);
                 const bool elected = elect_one();
                 if (elected && is_a && rank == 0) mbar_expect_tx(&full_bar[stage], pair_tx);
                 const uint32_t full_leader = map_to_cta(&full_bar[stage], leader);
                 uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kTcABytes;
-                const int kc = (kb >= sg.kb_per_part ? kb - sg.kb_per_part : kb) * kTcBlockK;
+                const int kc = (kb - part * kbp) * kTcBlockK;
                 if (!elected) {
                 } else if (is_a) {
-                    if (kFuPN > 1) tma_load_2d_pair_mc(maps + (second ? kMapA1 : kMapA0), full_leader, sa + qn * kFuARows * 128, kc, arow_of(t.m), mask_a);
-                    else tma_load_2d_pair(maps + (second ? kMapA1 : kMapA0), full_leader, sa, kc, arow_of(t.m));
+                    tma_load_2d_pair(maps + (hp ? kMapA1 : kMapA0), full_leader, sa, kc, hp ? a1_row : a0_row);
                 } else {
-                    tma_load_2d_pair(maps + (second ? kMapB1 : kMapB0), full_leader, sb, kc, n * 2 * brows + (int) rank * brows);
+                    tma_load_2d_pair(maps + (hp ? kMapB1 : kMapB0), full_leader, sb, kc, t.n * 2 * brows + (int) rank * brows);
                 }
                 __syncwarp();
-                if (is_a && kb == par) {
+                if (kb == par && (is_a || warp == 4)) {
                     const int g1 = g + num_clusters;
                     if (g1 < total) {
                         const FuTile t1 = fu_decode(args, g1);
-                        if (args.seg[t1.s].dep >= 0) {
-                            seen = ld_relaxed_gpu(args.counters + (size_t) args.seg[t1.s].dep * args.num_m_tiles + t1.m);
-                            seen_valid = true;
-                        }
-                    }
-                }
-                if (warp == 1 && kb == par) {
-                    // h(t-1) operands come from HBM (written a whole step ago): my 64 rows of the NEXT tile's (and, for the
-                    // cluster's first tile, this tile's) operand are one contiguous range; request it into L2 now, a whole
-                    // mainloop ahead -- after this tile's first load so that the request does not queue in front of it
-                    const uint32_t bytes = (uint32_t) (kFuARows * args.H * 2);
-                    if (elect_one()) {
-                        if (pit == 0 && gru) prefetch_l2(sg.a1 + (size_t) arow_of(t.m) * args.H, bytes);
-                        const int g1 = g + num_clusters;
-                        if (g1 < total) {
-                            const FuTile t1 = fu_decode(args, g1);
-                            if (args.seg[t1.s].mode == kTcGru) prefetch_l2(args.seg[t1.s].a1 + (size_t) arow_of(t1.m) * args.H, bytes);
+                        if (is_a) {
+                            const unsigned *ctr = nullptr;
+                            unsigned target = 0;
+                            if (fu_dep_x(args, t1, ctr, target)) seen_x = ld_relaxed_gpu(ctr);
+                            if (fu_dep_h(args, t1, ctr, target)) seen_h = ld_relaxed_gpu(ctr);
+                            have_seen = true;
+                        } else if (args.seg[t1.s].mode == kTcGru && elect_one()) {
+                            // h(t-1) operands may have to come from HBM (written a whole step ago): my 128 rows of the next
+                            // tile's operand are one contiguous range; request it into L2 now, a whole mainloop ahead
+                            prefetch_l2(args.seg[t1.s].a1[t1.par] + (size_t) (t1.m * kTcPairM + arow) * args.H, (uint32_t) (kTcBlockM * args.H * 2));
                         }
                     }
                     __syncwarp();
@@ -277,6 +324,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 const bool gru = sg.mode == kTcGru;
                 const int num_kb = sg.kb_per_part * sg.parts, kbp = sg.kb_per_part;
                 const uint32_t idesc = gru ? make_idesc(256, kGruRows) : make_idesc(256, kFuLinN);
+                const int hpart = gru ? (sg.x_first ? 1 : 0) : -1;
                 const int ab = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[ab], aphase);      // both CTAs' epilogues have released (and cleared) this buffer
                 tc_fence_after();
@@ -285,14 +333,15 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 // The whole k loop runs in ONE elected lane: every instruction between two k-blocks (barrier test, descriptor
                 // arithmetic, moves into uniform registers) is serial latency of this thread and shows up one-for-one in the
                 // k-block time, so nothing is re-elected, re-synchronised or re-selected per k-block, and the loop is split by
-                // operand part to keep its body branch-free.  GRU: the h part comes first and initialises columns [r | z | n_h];
-                // the x part accumulates into [n_x | r | z], whose n_x columns the epilogue left zeroed.
+                // operand part to keep its body branch-free.  GRU: the h part writes columns [r | z | n_h], the x part
+                // [n_x | r | z]; whichever runs first overwrites its columns, the other accumulates -- its private n columns
+                // were left zeroed by the epilogue.
                 int stage = (int) (kb_total % kStages), phase = (int) ((kb_total / kStages) & 1);
                 kb_total += (unsigned) num_kb;
                 if (elect_one()) {
                     for (int part = 0; part < sg.parts; ++part) {
-                        const uint32_t dk = (gru && part == 0) ? d + kGruUnits : d;
-                        const uint32_t first = (gru && part == 1) ? 1u : 0u;    // linear tiles and the GRU h part start from zero
+                        const uint32_t dk = part == hpart ? d + kGruUnits : d;
+                        const uint32_t first = part == 0 ? 0u : 1u;
                         for (int kb = 0; kb < kbp; ++kb) {
                             mbar_wait(&full_bar[stage], phase);
                             tc_fence_after();
@@ -301,7 +350,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
 #pragma unroll
                             for (int k = 0; k < kTcBlockK / 16; ++k)    // +32 B per 16-element k-step
                                 umma_bf16_pair(dk, adesc0 + so + 2 * k, bdesc0 + so + 2 * k, idesc, (kb | k) != 0 ? 1u : first);
-                            umma_commit_pair(&empty_bar[stage], all_mask);   // partners multicast into my slots, so everyone must know
+                            umma_commit_pair(&empty_bar[stage], pair_mask);
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -314,9 +363,11 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
     } else if (warp == kTcStateWarp) {
         // ===================================================== state warp: one thread moves the staging boxes of the GRU tiles
         // (two passes of 32 units each).  `cur` walks the passes in order (wait until staged, store fp32 + bf16 h(t), commit);
-        // `ahead` runs two passes in front and requests the fp32 h(t-1) box of that pass into the buffer `cur` just drained,
-        // a whole mainloop before the epilogue needs it.  After a tile's second pass it waits for the stores to COMPLETE and
-        // bumps the segment's counter for the m tile, which releases the dependent tiles of the next segment.
+        // `ahead` runs up to two passes in front and requests the fp32 h(t-1) box of that pass into the buffer `cur` has
+        // drained -- the slice was written by the same tile position one step earlier, so the tile's (h) dependency must hold
+        // first.  That test never blocks while a staged pass of this pair may still be unstored (the dependency can be this very
+        // pair's previous tile); it blocks only when the pass is the next one to be needed.  After a tile's second pass the warp
+        // waits for the stores to COMPLETE and bumps the segment's counter for the m tile, which releases the dependent tiles.
         pdl_wait();
         if (elect_one()) {
             const int row0 = (int) rank * kTcBlockM;
@@ -324,7 +375,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 int g, c;
                 FuTile t;
             };
-            auto start = [&](PassIter &p, int g) {           // first pass of the cluster's next GRU tile at or after g
+            auto start = [&](PassIter &p, int g) {           // first pass of the pair's next GRU tile at or after g
                 for (; g < total; g += num_clusters) {
                     p.t = fu_decode(args, g);
                     if (args.seg[p.t.s].mode == kTcGru) break;
@@ -335,88 +386,91 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             auto advance = [&](PassIter &p) {
                 if (++p.c == 2) start(p, p.g + num_clusters);
             };
-            auto arm = [&](const PassIter &p, int buf) {     // request the fp32 h(t-1) box of pass p into staging buffer `buf`
-                mbar_expect_tx(&box_ready[buf], kFuBoxF32);
-                tma_load_2d_local(args.maps + p.t.s * kFuMapsPerSeg + kMapHp, &box_ready[buf], s_f32 + buf * kFuBoxF32,
-                                  (p.t.n0 + qn) * kGruUnits + 32 * p.c, p.t.m * kTcPairM + row0);
-            };
             PassIter cur, ahead;
             start(cur, cluster_id);
             ahead = cur;
-            for (int b = 0; b < 2 && ahead.g < total; ++b) {
-                arm(ahead, b);
+            unsigned armed = 0, pc = 0;      // passes requested / stored so far; pass q uses staging buffer q & 1
+            auto try_arm = [&](bool block) {
+                if (ahead.g >= total || armed >= pc + 2) return;          // nothing left, or the buffer still holds an unstored pass
+                const unsigned *ctr = nullptr;
+                unsigned target = 0;
+                if (fu_dep_h(args, ahead.t, ctr, target) && (int) (ld_relaxed_gpu(ctr) - target) < 0) {
+                    if (!block) return;
+                    fu_wait_counter(ctr, target);
+                }
+                const int buf = (int) (armed & 1);
+                mbar_expect_tx(&box_ready[buf], kFuBoxF32);
+                tma_load_2d_local(args.maps + (size_t) (ahead.t.par * args.nseg + ahead.t.s) * kFuMapsPerSeg + kMapHp, &box_ready[buf],
+                                  s_f32 + buf * kFuBoxF32, ahead.t.n * kGruUnits + 32 * ahead.c, ahead.t.m * kTcPairM + row0);
                 advance(ahead);
-            }
-            unsigned pc = 0;
+                ++armed;
+            };
             int it = 0;
             while (cur.g < total) {
+                if (armed <= pc) try_arm(true);      // the pass the epilogue needs next: everything before it is stored and signalled
+                try_arm(false);
                 const int buf = (int) (pc & 1);
-                const FuSeg &sg = args.seg[cur.t.s];
-                const CUtensorMap *maps = args.maps + cur.t.s * kFuMapsPerSeg;
-                const int row = cur.t.m * kTcPairM + row0, col = (cur.t.n0 + qn) * kGruUnits + 32 * cur.c;
+                const CUtensorMap *maps = args.maps + (size_t) (cur.t.par * args.nseg + cur.t.s) * kFuMapsPerSeg;
+                const int row = cur.t.m * kTcPairM + row0, col = cur.t.n * kGruUnits + 32 * cur.c;
                 mbar_wait(&staged[buf], (pc >> 1) & 1);
+                if (cur.c == 0) fu_wait_war(args, cur.t);
                 tma_store_2d(maps + kMapHn, s_f32 + buf * kFuBoxF32, col, row);
                 tma_store_2d(maps + kMapHb, s_b16 + buf * kFuBoxB16, col, row);
                 bulk_commit();
                 KTRACE(it * 48 + 9 + (cur.c & 1) * 2);
-                if (ahead.g < total) {
-                    bulk_wait_read();                        // the stores have read buffer `buf`
-                    arm(ahead, buf);
-                    advance(ahead);
-                }
+                bulk_wait_read();                            // the stores have read buffer `buf`
+                ++pc;
                 if (cur.c == 1) {
-                    if (sg.done >= 0) {
-                        bulk_wait_all();                     // this tile's rows are in global memory
-                        fence_proxy_async_all();
-                        red_release_gpu(args.counters + (size_t) sg.done * args.num_m_tiles + cur.t.m, 1u);
-                    }
+                    bulk_wait_all();                         // this tile's rows are in global memory
+                    fence_proxy_async_all();
+                    fu_signal_done(args, cur.t);
                     ++it;
                 }
                 advance(cur);
-                ++pc;
+                try_arm(false);                              // the pass two ahead, into the buffer just drained
             }
-            bulk_wait_read();                                // shared memory must outlive the last stores' reads (kernel completion covers the writes)
-            mbar_arrive(gru_done);                           // ... and from here on the decoder tiles may stage in the GRU boxes
         }
         __syncwarp();
     } else if (warp == kFuLinWarp) {
         // ===================================================== linear-tile store warp: encoder / decoder outputs leave through
         // their own 32 KB staging region, so they never compete with the GRU passes for staging buffers: the encoder's whole
-        // [128][128] bf16 tile of this CTA fits; the decoder's [128][128] fp32 tile takes the two fp32 GRU boxes as well, which
-        // are idle by then (a pair's decoder tiles come after all its GRU tiles; `gru_done`).  Per tile: wait until the epilogue
-        // warps have staged it, TMA-store its boxes, free the region once they have been read; after an encoder tile, wait
-        // for the stores to complete and release the dependent GRU tiles.
+        // [128][128] bf16 tile of this CTA fits; the decoder's [128][128] fp32 tile takes two rounds of 64 columns.  Per round:
+        // wait until the epilogue warps have staged it, TMA-store its boxes, free the region once they have been read; after
+        // the tile's last round, wait for the stores to complete and release the dependent tiles.
         pdl_wait();
         if (elect_one()) {
             const int row0 = (int) rank * kTcBlockM;
-            unsigned lc = 0;
+            unsigned n16 = 0, n8 = 0;
             for (int g = cluster_id; g < total; g += num_clusters) {
                 const FuTile t = fu_decode(args, g);
                 const FuSeg &sg = args.seg[t.s];
                 if (sg.mode == kTcGru) continue;
-                const CUtensorMap *map = args.maps + t.s * kFuMapsPerSeg + kMapHn;
-                const int row = t.m * kTcPairM + row0, col = (t.n0 + qn) * kFuLinN;
-                mbar_wait(lin_staged, lc & 1);
-                if (sg.mode == kTcEnc) {           // two boxes of 64 bf16 columns
+                const CUtensorMap *map = args.maps + (size_t) (t.par * args.nseg + t.s) * kFuMapsPerSeg + kMapHn;
+                const int col = t.n * kFuLinN;
+                if (sg.mode == kTcEnc) {           // two boxes of 64 bf16 columns into ring slot G % ring
+                    const int row = t.m * kTcPairM + row0 + (int) (t.g % args.e_ring) * args.Bp;
+                    mbar_wait(lin_staged16, n16++ & 1);
+                    fu_wait_war(args, t);
                     tma_store_2d(map, s_lin, col, row);
                     tma_store_2d(map, s_lin + kFuBoxF32, col + 64, row);
-                } else {                           // four boxes of 32 fp32 columns: two in the linear region, two in the GRU boxes
-                    tma_store_2d(map, s_lin, col, row);
-                    tma_store_2d(map, s_lin + kFuBoxF32, col + 32, row);
-                    tma_store_2d(map, s_f32, col + 64, row);
-                    tma_store_2d(map, s_f32 + kFuBoxF32, col + 96, row);
+                    bulk_commit();
+                    bulk_wait_read();
+                    mbar_arrive(lin_free);
+                } else {                           // two rounds of two boxes of 32 fp32 columns into mask slot t
+                    const int row = t.m * kTcPairM + row0 + t.t * args.Bp;
+                    for (int r = 0; r < 2; ++r) {
+                        mbar_wait(lin_staged8, n8++ & 1);
+                        tma_store_2d(map, s_lin, col + 64 * r, row);
+                        tma_store_2d(map, s_lin + kFuBoxF32, col + 64 * r + 32, row);
+                        bulk_commit();
+                        bulk_wait_read();
+                        mbar_arrive(lin_free);
+                    }
                 }
-                bulk_commit();
-                bulk_wait_read();
-                mbar_arrive(lin_free);
-                ++lc;
-                if (sg.done >= 0) {
-                    bulk_wait_all();                         // this tile's rows are in global memory
-                    fence_proxy_async_all();
-                    red_release_gpu(args.counters + (size_t) sg.done * args.num_m_tiles + t.m, 1u);
-                }
+                bulk_wait_all();                             // this tile's rows are in global memory
+                fence_proxy_async_all();
+                fu_signal_done(args, t);
             }
-            bulk_wait_read();                                // every store has read its staging box; the grid's completion orders the writes
         }
         __syncwarp();
     } else if (warp >= 5 && warp < kTcStateWarp) {
@@ -426,11 +480,14 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         const int quarter = warp & 3, part = (warp - 5) >> 2, te = threadIdx.x - 160;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
         uint32_t empty_leader[2] = {map_to_cta(&tmem_empty[0], leader), map_to_cta(&tmem_empty[1], leader)};
-        // hand both buffers to the MMA issuer for the first time, with the GRU n_x columns cleared (linear tiles start from zero anyway)
+        // hand both buffers to the MMA issuer for the first time, with the GRU n_x and n_h columns cleared
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            tmem_zero8(lane_base + b * kTcAccCols + part * 16);
-            tmem_zero8(lane_base + b * kTcAccCols + part * 16 + 8);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tmem_zero8(lane_base + b * kTcAccCols + h * 3 * kGruUnits + part * 16);
+                tmem_zero8(lane_base + b * kTcAccCols + h * 3 * kGruUnits + part * 16 + 8);
+            }
         }
         tmem_st_wait();
         tc_fence_before();
@@ -443,12 +500,12 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         const int row_in_cta = quarter * 32 + lane;
         const int sw = row_in_cta & 7;
         constexpr float kL2e = 1.4426950408889634f;
-        unsigned pc = 0, lc = 0;       // GRU passes / linear rounds so far: staging buffer and barrier phase
+        unsigned pc = 0, lf = 0;       // GRU passes / linear rounds so far: staging buffer and barrier phase
         int it = 0;
         for (int g = cluster_id; g < total; g += num_clusters, ++it) {
             const FuTile t = fu_decode(args, g);
             const FuSeg &sg = args.seg[t.s];
-            const int mode = sg.mode, n = t.n0 + qn;
+            const int mode = sg.mode, n = t.n;
             const int ab = it & 1, aphase = (it >> 1) & 1;
             float *sb = s_bias + ab * 256;
             if (mode == kTcGru) {
@@ -472,8 +529,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (mode != kTcGru) {
                 // linear tile: my warp owns 32 of the 128 outputs (columns part * 32 ..), one row per thread.  The accumulator
-                // buffer is handed back after four TMEM loads; the outputs are staged in 128B-swizzled boxes (the linear
-                // staging region, plus the idle GRU boxes for the decoder's fp32 tile) and stored by the linear store warp.
+                // buffer is handed back after four TMEM loads; the outputs are staged in 128B-swizzled boxes of the linear
+                // staging region and stored by the linear store warp.
                 float acc[32];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tmem_ld8(t0 + part * 32 + 8 * j, *reinterpret_cast<float(*)[8]>(acc + 8 * j));
@@ -491,23 +548,27 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                     const float v = acc[i] + sb[part * 32 + i];
                     acc[i] = mode == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
                 }
-                mbar_wait(lin_free, (lc & 1) ^ 1);           // the previous linear tile's stores have read the staging boxes
                 if (mode == kTcEnc) {                        // box part / 2 holds columns 64 (part / 2) ..; my 32 columns = 4 chunks of 8 bf16
+                    mbar_wait(lin_free, (lf & 1) ^ 1);       // the previous linear round's stores have read the staging boxes
                     uint8_t *rowp = s_lin + (part >> 1) * kFuBoxF32 + row_in_cta * 128;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + j) ^ sw) << 4)) = pack_bf16x8(acc + 8 * j);
-                } else {                                     // my 32 fp32 columns = one box of 8 chunks of 4: parts 0,1 in the linear region, 2,3 in the GRU boxes
-                    if (part >= 2) mbar_wait(gru_done, 0);
-                    uint8_t *rowp = (part < 2 ? s_lin : s_f32) + (part & 1) * kFuBoxF32 + row_in_cta * 128;
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(lin_staged16);
+                    lf += 1;
+                } else {                                     // round part / 2, box part & 1: my 32 fp32 columns = 8 chunks of 4
+                    mbar_wait(lin_free, ((lf + (unsigned) (part >> 1)) & 1) ^ 1);
+                    uint8_t *rowp = s_lin + (part & 1) * kFuBoxF32 + row_in_cta * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4 *>(rowp + ((j ^ sw) << 4)) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(lin_staged8);
+                    lf += 2;
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(lin_staged);
-                ++lc;
                 continue;
             }
             // GRU tile: two passes of 32 units through the staging buffers
@@ -529,7 +590,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 }
                 tmem_ld_wait();
                 if (te == 0) KTRACE(it * 48 + 8 + c * 2);
-                tmem_zero8(t0 + cu);                         // n_x columns must be zero when the next GRU tile's x part accumulates into them
+                tmem_zero8(t0 + cu);                         // the n columns only one operand part touches must be zero when the
+                tmem_zero8(t0 + 3 * kGruUnits + cu);         // next GRU tile's second part accumulates into them
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     // r = 1/(1+er), z = 1/(1+ez) share one reciprocal: 5 MUFU ops per unit.  Arguments are clamped so that
@@ -561,26 +623,27 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             }
         }
     }
-    if (threadIdx.x == 0) KTRACE(1022);
+    if (threadIdx.x == 0) KTRACE_HDR(1022);
     tc_fence_before();
     cluster_sync_all();      // the peer's smem / TMEM are read and written by the leader's MMAs: leave together
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, 2 * kTcAccCols);
     }
-    if (threadIdx.x == 0) KTRACE(1023);
+    if (threadIdx.x == 0) KTRACE_HDR(1023);
 #undef KTRACE
+#undef KTRACE_HDR
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side: tensor maps and segment tables for both state parities, the dependency counters, the launch
 struct FuPlan {
-    int nseg = 0, max_clusters = 0, num_sms = 0;
+    int nseg = 0, max_clusters = 0, num_sms = 0, tcap = 1;
     __nv_bfloat16 *wih_p[kMaxLayers] = {}, *whh_p[kMaxLayers] = {};   // GRU weights packed per 64-unit tile (pack_gru_weights_kernel)
-    unsigned epoch = 0;
+    long long epoch = 0;              // steps completed by accepted launches
     unsigned *counters = nullptr;
-    CUtensorMap *d_maps[2] = {};      // [parity][nseg][kFuMapsPerSeg]
-    FuArgs args[2];                   // by parity of the buffer that holds h(t-1)
+    CUtensorMap *d_maps = nullptr;    // [parity][nseg][kFuMapsPerSeg]
+    FuArgs args;
     long long *trace = nullptr;       // 2 x 1024 clock64 slots of CTAs 0 and 1 (allocated when KOALA_FU_TRACE_BUF=1; written by -DKOALA_FU_TRACE=1 builds), else nullptr
 };
 
@@ -591,12 +654,12 @@ static void fu_plan_destroy(FuPlan *f) {
         if (f->whh_p[l]) cudaFree(f->whh_p[l]);
     }
     if (f->counters) cudaFree(f->counters);
-    for (int i = 0; i < 2; i++)
-        if (f->d_maps[i]) cudaFree(f->d_maps[i]);
+    if (f->d_maps) cudaFree(f->d_maps);
     if (f->trace) cudaFree(f->trace);
     delete f;
 }
 
+// `m.feat` / `m.mask` hold m.tcap step slots of [Bp] rows, `m.e` holds m.e_ring slots
 static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
     if (m.H % 256 != 0 || m.Bp % kTcPairM != 0) {
         *why = "hidden size must be a multiple of 256 and the padded stream count a multiple of 256 for the tensor-core path";
@@ -614,6 +677,7 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
     const size_t H = m.H, Bp = m.Bp, L = m.L, LBH = Bp * H;
     const int mt = m.Bp / kTcPairM, nseg = m.L + 2;
     f->nseg = nseg;
+    f->tcap = m.tcap;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&f->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -625,72 +689,14 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
         pack_gru_weights_kernel<<<(unsigned) (3 * H), 64>>>(m.whh[l], f->whh_p[l], (int) H, 0, 1, 2);   // r | z | n
     }
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
-    ok = ok && cudaMalloc((void **) &f->counters, (size_t) nseg * mt * sizeof(unsigned)) == cudaSuccess &&
-              cudaMemset(f->counters, 0, (size_t) nseg * mt * sizeof(unsigned)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **) &f->counters, (size_t) nseg * mt * kFuSlots * sizeof(unsigned)) == cudaSuccess &&
+              cudaMemset(f->counters, 0, (size_t) nseg * mt * kFuSlots * sizeof(unsigned)) == cudaSuccess;
     if (const char *tr = getenv("KOALA_FU_TRACE_BUF")) {
         if (tr[0] == '1' && cudaMalloc((void **) &f->trace, 2048 * sizeof(long long)) == cudaSuccess) cudaMemset(f->trace, 0, 2048 * sizeof(long long));
     }
-    for (int cur = 0; cur < 2 && ok; cur++) {
-        const int nxt = cur ^ 1;
-        std::vector<CUtensorMap> maps((size_t) nseg * kFuMapsPerSeg);
-        FuArgs &a = f->args[cur];
-        memset(&a, 0, sizeof(a));
-        a.nseg = nseg; a.num_m_tiles = mt; a.H = m.H; a.counters = f->counters; a.trace = f->trace;
-        int tile = 0;
-        for (int s = 0; s < nseg && ok; s++) {
-            FuSeg &sg = a.seg[s];
-            CUtensorMap *mp = maps.data() + (size_t) s * kFuMapsPerSeg;
-            bool used[kFuMapsPerSeg] = {};
-            auto put = [&](int k, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool f32 = false, bool plain32 = false) {
-                used[k] = true;
-                ok = ok && encode_2d(fn, &mp[k], base, rows, cols, box_rows, f32, plain32);
-            };
-            sg.tile_begin = tile;
-            sg.dep = s == 0 ? -1 : s - 1;
-            sg.done = s == nseg - 1 ? -1 : s;
-            if (s == 0) {                                  // encoder: e = relu(feat W_enc^T + b)
-                sg.mode = kTcEnc; sg.n_ctiles = m.H / kFuLinN / kFuPN; sg.kb_per_part = kBins / kTcBlockK; sg.parts = 1;
-                sg.bias0 = m.enc_b;
-                put(kMapA0, m.feat, Bp, kBins, kFuARows);
-                put(kMapB0, m.enc_w, H, kBins, kFuLinN / 2);
-                put(kMapHn, m.e, Bp, H, kTcBlockM);                  // store map: boxes of 64 bf16 columns x 128 rows, 128B swizzle
-            } else if (s == nseg - 1) {                    // decoder: mask = sigmoid(h_{L-1}(t) W_dec^T + b)
-                sg.mode = kTcDec; sg.n_ctiles = kBins / kFuLinN / kFuPN; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 1;
-                sg.bias0 = m.dec_b;
-                put(kMapA0, m.hb[nxt] + (L - 1) * LBH, Bp, H, kFuARows);
-                put(kMapB0, m.dec_w, kBins, H, kFuLinN / 2);
-                put(kMapHn, m.mask, Bp, kBins, kTcBlockM, true);    // store map: boxes of 32 fp32 columns x 128 rows, 128B swizzle
-            } else {                                       // GRU layer l
-                const size_t l = s - 1;
-                sg.mode = kTcGru; sg.n_ctiles = m.H / kGruUnits / kFuPN; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 2;
-                sg.bias0 = m.bih[l]; sg.bias1 = m.bhh[l]; sg.a1 = m.hb[cur] + l * LBH;
-                put(kMapA0, l == 0 ? m.e : m.hb[nxt] + (l - 1) * LBH, Bp, H, kFuARows);
-                put(kMapA1, m.hb[cur] + l * LBH, Bp, H, kFuARows);
-                put(kMapB0, f->wih_p[l], 3 * H, H, kGruRows / 2);
-                put(kMapB1, f->whh_p[l], 3 * H, H, kGruRows / 2);
-                put(kMapHp, m.h[cur] + l * LBH, Bp, H, kTcBlockM, true);
-                put(kMapHn, m.h[nxt] + l * LBH, Bp, H, kTcBlockM, true);
-                put(kMapHb, m.hb[nxt] + l * LBH, Bp, H, kTcBlockM, false, true);
-            }
-            // rows of an m tile are written by every CTA (2 per pair tile) of every n tile of the previous segment
-            sg.dep_per_step = s == 0 ? 0u : (unsigned) (a.seg[s - 1].n_ctiles * kFuPN * 2);
-            for (int k = 0; k < kFuMapsPerSeg; k++)        // unused slots: any valid descriptor (they are only prefetched)
-                if (!used[k]) mp[k] = mp[kMapA0];
-            tile += mt * sg.n_ctiles;
-        }
-        a.total_tiles = tile;
-        ok = ok && cudaMalloc((void **) &f->d_maps[cur], maps.size() * sizeof(CUtensorMap)) == cudaSuccess &&
-             cudaMemcpy(f->d_maps[cur], maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess;
-        a.maps = f->d_maps[cur];
-    }
     ok = ok && cudaFuncSetAttribute(tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes) == cudaSuccess;
-    if (!ok) {
-        *why = "setting up the fused mask-estimator kernel failed (tensor maps / counters / shared memory size)";
-        cudaGetLastError();
-        fu_plan_destroy(f);
-        return false;
-    }
-    {
+    int resident_pairs = f->num_sms / kFuCluster;      // CTA pairs the device can hold at once
+    if (ok) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned) (kFuCluster * f->num_sms));
         cfg.blockDim = dim3(kFuThreads);
@@ -701,21 +707,97 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
         cfg.attrs = attr; cfg.numAttrs = 1;
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, tc_fused_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = f->num_sms / kFuCluster - 4; }
+        resident_pairs = n;
         if (const char *e = getenv("KOALA_FU_CLUSTERS")) n = std::max(1, std::min(n, atoi(e)));
         f->max_clusters = n;
+    }
+    std::vector<CUtensorMap> maps((size_t) 2 * nseg * kFuMapsPerSeg);
+    FuArgs &a = f->args;
+    memset(&a, 0, sizeof(a));
+    a.nseg = nseg; a.num_m_tiles = mt; a.H = m.H; a.Bp = m.Bp; a.e_ring = m.e_ring; a.counters = f->counters; a.trace = f->trace;
+    int tile = 0;
+    for (int s = 0; s < nseg; s++) {
+        FuSeg &sg = a.seg[s];
+        sg.tile_begin = tile;
+        if (s == 0) {                                  // encoder: e = relu(feat W_enc^T + b)
+            sg.mode = kTcEnc; sg.n_tiles = m.H / kFuLinN; sg.kb_per_part = kBins / kTcBlockK; sg.parts = 1;
+            sg.bias0 = m.enc_b;
+        } else if (s == nseg - 1) {                    // decoder: mask = sigmoid(h_{L-1}(t) W_dec^T + b)
+            sg.mode = kTcDec; sg.n_tiles = kBins / kFuLinN; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 1;
+            sg.bias0 = m.dec_b;
+        } else {                                       // GRU layer l
+            const size_t l = s - 1;
+            sg.mode = kTcGru; sg.n_tiles = m.H / kGruUnits; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 2;
+            sg.bias0 = m.bih[l]; sg.bias1 = m.bhh[l];
+            for (int par = 0; par < 2; par++) sg.a1[par] = m.hb[par] + l * LBH;
+        }
+        sg.inc = (unsigned) (2 * sg.n_tiles);          // the rows of an m tile are written by both CTAs of every n tile
+        tile += mt * sg.n_tiles;
+    }
+    a.tiles_per_step = tile;
+    // small batches are bound by the latency of the recurrence GRU_l(t-1) -> GRU_l(t): run the x part (whose operands exist
+    // earlier) first, so that only the h half of the k loop follows the wait.  KOALA_FU_XFIRST=0/1 overrides.
+    bool x_first = tile <= resident_pairs;       // (a property of the model, the stream count and the device: results do not depend on KOALA_FU_CLUSTERS)
+    if (const char *e = getenv("KOALA_FU_XFIRST")) x_first = e[0] == '1';
+    for (int s = 1; s < nseg - 1; s++) a.seg[s].x_first = x_first ? 1 : 0;
+    for (int cur = 0; cur < 2 && ok; cur++) {          // cur = parity of the buffers that hold h(t-1)
+        const int nxt = cur ^ 1;
+        for (int s = 0; s < nseg && ok; s++) {
+            CUtensorMap *mp = maps.data() + (size_t) (cur * nseg + s) * kFuMapsPerSeg;
+            bool used[kFuMapsPerSeg] = {};
+            auto put = [&](int k, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool f32 = false, bool plain32 = false) {
+                used[k] = true;
+                ok = ok && encode_2d(fn, &mp[k], base, rows, cols, box_rows, f32, plain32);
+            };
+            if (s == 0) {
+                put(kMapA0, m.feat, (uint64_t) m.tcap * Bp, kBins, kTcBlockM);
+                put(kMapB0, m.enc_w, H, kBins, kFuLinN / 2);
+                put(kMapHn, m.e, (uint64_t) m.e_ring * Bp, H, kTcBlockM);     // store map: boxes of 64 bf16 columns x 128 rows, 128B swizzle
+            } else if (s == nseg - 1) {
+                put(kMapA0, m.hb[nxt] + (L - 1) * LBH, Bp, H, kTcBlockM);
+                put(kMapB0, m.dec_w, kBins, H, kFuLinN / 2);
+                put(kMapHn, m.mask, (uint64_t) m.tcap * Bp, kBins, kTcBlockM, true);    // store map: boxes of 32 fp32 columns x 128 rows, 128B swizzle
+            } else {
+                const size_t l = s - 1;
+                if (l == 0) put(kMapA0, m.e, (uint64_t) m.e_ring * Bp, H, kTcBlockM);
+                else put(kMapA0, m.hb[nxt] + (l - 1) * LBH, Bp, H, kTcBlockM);
+                put(kMapA1, m.hb[cur] + l * LBH, Bp, H, kTcBlockM);
+                put(kMapB0, f->wih_p[l], 3 * H, H, kGruRows / 2);
+                put(kMapB1, f->whh_p[l], 3 * H, H, kGruRows / 2);
+                put(kMapHp, m.h[cur] + l * LBH, Bp, H, kTcBlockM, true);
+                put(kMapHn, m.h[nxt] + l * LBH, Bp, H, kTcBlockM, true);
+                put(kMapHb, m.hb[nxt] + l * LBH, Bp, H, kTcBlockM, false, true);
+            }
+            for (int k = 0; k < kFuMapsPerSeg; k++)        // unused slots: any valid descriptor (they are only prefetched)
+                if (!used[k]) mp[k] = mp[kMapA0];
+        }
+    }
+    ok = ok && cudaMalloc((void **) &f->d_maps, maps.size() * sizeof(CUtensorMap)) == cudaSuccess &&
+         cudaMemcpy(f->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess;
+    a.maps = f->d_maps;
+    if (!ok) {
+        *why = "setting up the fused mask-estimator kernel failed (tensor maps / counters / shared memory size)";
+        cudaGetLastError();
+        fu_plan_destroy(f);
+        return false;
     }
     *out = f;
     return true;
 }
 
-// one mask-estimator step = one launch: hb[cur] / h[cur] hold state t-1, results go to hb[cur ^ 1] / h[cur ^ 1]
-static int fu_masknet_step(FuPlan *f, int cur, cudaStream_t st) {
-    FuArgs &a = f->args[cur];
-    a.epoch = f->epoch + 1;
+// `steps` mask-estimator steps = one launch: hb[cur] / h[cur] hold the state before the first step; features are read from
+// slots 0..steps-1 of `feat`, masks written to the same slots of `mask`; the state ends up in the buffers of parity cur ^ (steps & 1)
+static int fu_masknet_steps(FuPlan *f, int cur, int steps, cudaStream_t st) {
+    FuArgs &a = f->args;
+    a.steps = steps;
+    a.cur0 = cur;
+    a.epoch0 = f->epoch;
+    a.total_tiles = steps * a.tiles_per_step;
     const int clusters = a.total_tiles < f->max_clusters ? a.total_tiles : f->max_clusters;
     // the epoch only advances with a launch that was accepted: the counters then stand at epoch * (increments per step), which
     // is what the next launch waits for (the caller reports the launch error through cudaGetLastError)
-    if (launch_pdl(true, tc_fused_kernel, dim3((unsigned) (kFuCluster * clusters)), dim3(kFuThreads), (size_t) kFuSmemBytes, st, a) == cudaSuccess) f->epoch = a.epoch;
+    if (launch_pdl(true, tc_fused_kernel, dim3((unsigned) (kFuCluster * clusters)), dim3(kFuThreads), (size_t) kFuSmemBytes, st, a) == cudaSuccess)
+        f->epoch += steps;
     return 1;
 }
 

@@ -28,12 +28,15 @@ __device__ __forceinline__ float feature_of(float re, float im) {
     return kFeatGain * __logf((re * re + im * im) * kFeatPowerScale + kFeatEps) + kFeatBias;
 }
 
-// Launch: block = 128, grid = ceil(n / (4 * streams per warp)) with streams per warp chosen by the engine so that the whole
-// grid is resident; warp w of CTA b walks streams s = b * 4 + w, += gridDim * 4.
-// spec: [n][512] fp32 packed (Re, Im of bins 0..255; the Im slot of bin 0 carries Re X[256]).
+// Launch: block = 128; the grid's warps walk the (frame, stream) items of the launch, item = t * n_streams + s, with a stride
+// of gridDim * 4 (the engine sizes the grid so that every warp gets about the same number of items).  A launch covers `frames`
+// consecutive frames of every stream (the chunk the fused mask-estimator kernel then walks in one launch): frame t's first
+// half is frame t - 1 of the caller's buffer, or the stream's tail (the last frame of the previous chunk / call) for t = 0.
+// The tail itself is rewritten by backend_kernel, after every reader of this launch is done.
+// spec: [frames][slot_rows][512] fp32 packed (Re, Im of bins 0..255; the Im slot of bin 0 carries Re X[256]); feat: [frames][slot_rows][256].
 template <typename FeatT>
 __global__ void __launch_bounds__(kStftWarps * 32, kStftCtasPerSm)
-frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__restrict__ spec,
+frontend_kernel(PcmView v, int n_streams, int frames, long long slot_rows, const int16_t *__restrict__ tail, float *__restrict__ spec,
                 FeatT *__restrict__ feat, const float2 *__restrict__ lane_tab) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
@@ -46,18 +49,19 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
     const int src = rev5((32 - cb) & 31);       // lane that holds the partner bins
     const bool lane0 = lane == 0;
 
-    for (int s = blockIdx.x * kStftWarps + warp; s < n_streams; s += gridDim.x * kStftWarps) {
+    const int items = n_streams * frames;
+    for (int idx = blockIdx.x * kStftWarps + warp; idx < items; idx += gridDim.x * kStftWarps) {
+        const int t = idx / n_streams, s = idx - t * n_streams;
         // frame = [previous input frame | this input frame] as 256 sample pairs; point p = lane + 32 j is pair p: j < 4 comes
-        // from the stream's tail, j >= 4 from the new samples, every load a coalesced 128-byte row
-        uint32_t *tail_s = reinterpret_cast<uint32_t *>(tail + (size_t) s * kFrame);
-        const uint32_t *in_s = reinterpret_cast<const uint32_t *>(v.in + (size_t) s * v.stride + (size_t) v.t * kFrame);
+        // from the previous frame, j >= 4 from the new samples, every load a coalesced 128-byte row
+        const int16_t *in_row = v.in + (size_t) s * v.stride + (size_t) (v.t + t) * v.frame_stride;
+        const uint32_t *prev_s = reinterpret_cast<const uint32_t *>(t == 0 ? tail + (size_t) s * kFrame : in_row - v.frame_stride);
+        const uint32_t *in_s = reinterpret_cast<const uint32_t *>(in_row);
         uint32_t u[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) u[j] = tail_s[lane + 32 * j];
+        for (int j = 0; j < 4; ++j) u[j] = prev_s[lane + 32 * j];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) u[4 + j] = __ldg(in_s + lane + 32 * j);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tail_s[lane + 32 * j] = u[4 + j];   // state: tail <- this frame (same words this lane read)
+        for (int j = 0; j < 4; ++j) u[4 + j] = in_s[lane + 32 * j];
 
         cpx z[8];
 #pragma unroll
@@ -69,8 +73,9 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
 
         // real-FFT split for k = cb + 32 m, m < 4, and 256 - k at once:
         //   E = (Z[k] + conj Z[256-k]) / 2,  O = (Z[k] - conj Z[256-k]) / 2i,  X[k] = E + W512^k O,  X[256-k] = conj(E - W512^k O)
-        float *spec_s = spec + (size_t) s * kNfft;
-        FeatT *feat_s = feat + (size_t) s * kBins;
+        const size_t row = (size_t) t * slot_rows + s;
+        float *spec_s = spec + row * kNfft;
+        FeatT *feat_s = feat + row * kBins;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const cpx zk = z[fft_reg_of_m(m)];
@@ -95,10 +100,61 @@ frontend_kernel(PcmView v, int n_streams, int16_t *__restrict__ tail, float *__r
     }
 }
 
-// Same launch shape as frontend_kernel.  mask: [n][256] fp32.  ola: [n][256] fp32 state.
+// Masked spectrum of one frame -> z[j] = 256 (y[2p] + i y[2p+1]), p = lane + 32 j (the 512 synthesis samples before windowing)
+__device__ __forceinline__ void synth_frame(const float *__restrict__ spec_s, const float *__restrict__ mask_s, cpx (&z)[8], const FftLane &c,
+                                            const float2 &sbase, int lane, int cb, int src, bool lane0) {
+    cpx ya[4], yb[4];
+    float ma[4], mb[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int ka = cb + 32 * m, kb = (m == 0 && lane0) ? 128 : 256 - ka;
+        const float2 a = *reinterpret_cast<const float2 *>(spec_s + 2 * ka), b = *reinterpret_cast<const float2 *>(spec_s + 2 * kb);
+        ya[m] = cpx{a.x, a.y};
+        yb[m] = cpx{b.x, b.y};
+        ma[m] = mask_s[ka];
+        mb[m] = mask_s[kb];
+    }
+    const float m255 = __shfl_sync(0xffffffffu, mb[0], 16);       // bin 255 = 256 - 1: partner bin of the lane with c = 1
+    cpx zp[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        // mask, then the inverse split: E = (Y[k] + conj Y[256-k]) / 2, O = (Y[k] - conj Y[256-k]) / 2 * conj(W512^k),
+        // Z[k] = E + i O, Z[256-k] = conj(E) + i conj(O)
+        const cpx yk = {ya[m].x * ma[m], ya[m].y * ((m == 0 && lane0) ? m255 : ma[m])};   // c = 0, m = 0: Im slot carries X[256], masked by mask[255]
+        const cpx yp = {yb[m].x * mb[m], yb[m].y * mb[m]};
+        const cpx E = {0.5f * (yk.x + yp.x), 0.5f * (yk.y - yp.y)};
+        const cpx D = {0.5f * (yk.x - yp.x), 0.5f * (yk.y + yp.y)};
+        const cpx O = cmulc(D, split_twiddle(sbase, m));
+        cpx zk = {E.x - O.y, E.y + O.x};
+        zp[m] = cpx{E.x + O.y, O.x - E.y};
+        if (m == 0 && lane0) {
+            zk = cpx{0.5f * (yk.x + yk.y), 0.5f * (yk.x - yk.y)};   // Z[0] from the packed real pair (X[0], X[256])
+            zp[0] = cpx{yp.x, -yp.y};                               // Z[128] = conj Y[128]
+        }
+        z[fft_reg_of_m(m)] = zk;
+    }
+    // the partner halves go home: register m' = 7 - m of lane `src`; c = 0 keeps its own (Z[128] and Z[256 - 32 m])
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const cpx t = shfl_c(zp[m], src);
+        const cpx own = m == 3 ? zp[0] : zp[m + 1];                // lane 0: register 7 - m holds bin 32 (7 - m) = 256 - 32 (m + 1); m = 3: bin 128
+        z[fft_reg_of_m(7 - m)] = lane0 ? own : t;
+    }
+    warp_fft256<true>(z, c, lane);
+}
+
+// Same launch shape; items are (run, stream) pairs, run r = frames [r * run, min(frames, (r + 1) * run)) of the launch: a warp
+// synthesises them one after the other and carries the overlap-add half in registers.  A run that does not start at the
+// launch's first frame first re-synthesises the frame before it to get that half (one extra inverse transform per run;
+// the engine makes runs as long as the stream count allows: 8192 streams x 16 frames = one run per stream).  The warp that
+// owns a stream's last frame stores the overlap-add state and the new analysis tail (= the last input frame, read before the
+// output is written: the caller's buffers may alias).  ola_in != ola_out unless the launch is one run per stream: other
+// warps still read ola_in.
+// mask: [frames][slot_rows][256] fp32.  ola: [n][256] fp32 state.
 __global__ void __launch_bounds__(kStftWarps * 32, kStftCtasPerSm)
-backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const float *__restrict__ mask,
-               float *__restrict__ ola, const float2 *__restrict__ lane_tab) {
+backend_kernel(PcmView v, int n_streams, int frames, int run, long long slot_rows, const float *__restrict__ spec,
+               const float *__restrict__ mask, const float *ola_in, float *ola_out, int16_t *__restrict__ tail,
+               const float2 *__restrict__ lane_tab) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
     FftLane c;
@@ -111,68 +167,58 @@ backend_kernel(PcmView v, int n_streams, const float *__restrict__ spec, const f
     const bool lane0 = lane == 0;
     constexpr float inv = 1.0f / 256.0f;
 
-    for (int s = blockIdx.x * kStftWarps + warp; s < n_streams; s += gridDim.x * kStftWarps) {
-        const float *spec_s = spec + (size_t) s * kNfft, *mask_s = mask + (size_t) s * kBins;
-        cpx ya[4], yb[4];
-        float ma[4], mb[4];
+    const int runs = (frames + run - 1) / run, items = n_streams * runs;
+    for (int idx = blockIdx.x * kStftWarps + warp; idx < items; idx += gridDim.x * kStftWarps) {
+        const int r = idx / n_streams, s = idx - r * n_streams;
+        const int ta = r * run, tb = min(frames, ta + run);
+        float2 o[4];           // second half of the previous synthesis frame
+        cpx z[8];
+        if (ta == 0) {         // the stream's state: issued early so the loads overlap the first transform
+            const float2 *ola2 = reinterpret_cast<const float2 *>(ola_in + (size_t) s * kFrame);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int ka = cb + 32 * m, kb = (m == 0 && lane0) ? 128 : 256 - ka;
-            const float2 a = *reinterpret_cast<const float2 *>(spec_s + 2 * ka), b = *reinterpret_cast<const float2 *>(spec_s + 2 * kb);
-            ya[m] = cpx{a.x, a.y};
-            yb[m] = cpx{b.x, b.y};
-            ma[m] = mask_s[ka];
-            mb[m] = mask_s[kb];
-        }
-        // OLA tail of this stream: issued early so the loads overlap the transform
-        float2 *ola2 = reinterpret_cast<float2 *>(ola + (size_t) s * kFrame);
-        float2 o[4];
+            for (int j = 0; j < 4; ++j) o[j] = ola2[lane + 32 * j];
+        } else {
+            const size_t row = (size_t) (ta - 1) * slot_rows + s;
+            synth_frame(spec + row * kNfft, mask + row * kBins, z, c, sbase, lane, cb, src, lane0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = ola2[lane + 32 * j];
-
-        const float m255 = __shfl_sync(0xffffffffu, mb[0], 16);       // bin 255 = 256 - 1: partner bin of the lane with c = 1
-        cpx z[8], zp[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            // mask, then the inverse split: E = (Y[k] + conj Y[256-k]) / 2, O = (Y[k] - conj Y[256-k]) / 2 * conj(W512^k),
-            // Z[k] = E + i O, Z[256-k] = conj(E) + i conj(O)
-            const cpx yk = {ya[m].x * ma[m], ya[m].y * ((m == 0 && lane0) ? m255 : ma[m])};   // c = 0, m = 0: Im slot carries X[256], masked by mask[255]
-            const cpx yp = {yb[m].x * mb[m], yb[m].y * mb[m]};
-            const cpx E = {0.5f * (yk.x + yp.x), 0.5f * (yk.y - yp.y)};
-            const cpx D = {0.5f * (yk.x - yp.x), 0.5f * (yk.y + yp.y)};
-            const cpx O = cmulc(D, split_twiddle(sbase, m));
-            cpx zk = {E.x - O.y, E.y + O.x};
-            zp[m] = cpx{E.x + O.y, O.x - E.y};
-            if (m == 0 && lane0) {
-                zk = cpx{0.5f * (yk.x + yk.y), 0.5f * (yk.x - yk.y)};   // Z[0] from the packed real pair (X[0], X[256])
-                zp[0] = cpx{yp.x, -yp.y};                               // Z[128] = conj Y[128]
+            for (int j = 4; j < 8; ++j) {
+                const float2 w = window_pair(we, wo, j);
+                o[j - 4] = make_float2(w.x * (z[j].x * inv), w.y * (z[j].y * inv));
             }
-            z[fft_reg_of_m(m)] = zk;
         }
-        // the partner halves go home: register m' = 7 - m of lane `src`; c = 0 keeps its own (Z[128] and Z[256 - 32 m])
+        for (int t = ta; t < tb; ++t) {
+            const size_t row = (size_t) t * slot_rows + s;
+            synth_frame(spec + row * kNfft, mask + row * kBins, z, c, sbase, lane, cb, src, lane0);
+            if (t == frames - 1) {                                     // state: tail <- the launch's last input frame
+                const uint32_t *in_s = reinterpret_cast<const uint32_t *>(v.in + (size_t) s * v.stride + (size_t) (v.t + t) * v.frame_stride);
+                uint32_t *tail_s = reinterpret_cast<uint32_t *>(tail + (size_t) s * kFrame);
+                uint32_t u[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const cpx t = shfl_c(zp[m], src);
-            const cpx own = m == 3 ? zp[0] : zp[m + 1];                // lane 0: register 7 - m holds bin 32 (7 - m) = 256 - 32 (m + 1); m = 3: bin 128
-            z[fft_reg_of_m(7 - m)] = lane0 ? own : t;
+                for (int j = 0; j < 4; ++j) u[j] = in_s[lane + 32 * j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tail_s[lane + 32 * j] = u[j];
+            }
+            // z[j] = 256 (y[2p] + i y[2p+1]), p = lane + 32 j.  j < 4: first half -> output; j >= 4: second half -> next overlap-add half.
+            uint32_t *out32 = reinterpret_cast<uint32_t *>(v.out + (size_t) s * v.out_stride + (size_t) (v.t + t) * v.out_frame_stride);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 w = window_pair(we, wo, j);
+                const float v0 = o[j].x + w.x * (z[j].x * inv), v1 = o[j].y + w.y * (z[j].y * inv);
+                short i0, i1;   // round-to-nearest-even + saturate, the oracle's rintf + clamp
+                asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i0) : "f"(v0));
+                asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i1) : "f"(v1));
+                out32[lane + 32 * j] = (uint32_t) (uint16_t) i0 | ((uint32_t) (uint16_t) i1 << 16);
+            }
+#pragma unroll
+            for (int j = 4; j < 8; ++j) {
+                const float2 w = window_pair(we, wo, j);
+                o[j - 4] = make_float2(w.x * (z[j].x * inv), w.y * (z[j].y * inv));
+            }
         }
-        warp_fft256<true>(z, c, lane);
-
-        // z[j] = 256 (y[2p] + i y[2p+1]), p = lane + 32 j.  j < 4: first half -> output; j >= 4: second half -> new OLA tail.
-        uint32_t *out32 = reinterpret_cast<uint32_t *>(v.out + (size_t) s * v.out_stride + (size_t) v.t * kFrame);
+        if (tb == frames) {
+            float2 *ola2 = reinterpret_cast<float2 *>(ola_out + (size_t) s * kFrame);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 w = window_pair(we, wo, j);
-            const float v0 = o[j].x + w.x * (z[j].x * inv), v1 = o[j].y + w.y * (z[j].y * inv);
-            short i0, i1;   // round-to-nearest-even + saturate, the oracle's rintf + clamp
-            asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i0) : "f"(v0));
-            asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(i1) : "f"(v1));
-            out32[lane + 32 * j] = (uint32_t) (uint16_t) i0 | ((uint32_t) (uint16_t) i1 << 16);
-        }
-#pragma unroll
-        for (int j = 4; j < 8; ++j) {
-            const float2 w = window_pair(we, wo, j);
-            ola2[lane + 32 * (j - 4)] = make_float2(w.x * (z[j].x * inv), w.y * (z[j].y * inv));
+            for (int j = 0; j < 4; ++j) ola2[lane + 32 * j] = o[j];
         }
     }
 }

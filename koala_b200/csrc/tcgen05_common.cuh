@@ -8,10 +8,11 @@
 // TMEM, gates / state update / activation fused into the epilogue that reads TMEM back with tcgen05.ld.
 //
 // GRU tile = 256 streams x 64 hidden units.  TMEM columns per accumulator buffer: [n_x 0..63 | r 64..127 | z 128..191 | n_h 192..255].
-//   h part (K = H): one N=192 MMA per k-step, packed W_hh rows ordered r|z|n, D column base 64 -> r, z, n_h   (runs first)
-//   x part (K = H): one N=192 MMA per k-step, packed W_ih rows ordered n|r|z, D column base  0 -> n_x, r, z   (accumulates)
-//   The accumulate flag is per instruction, so the n_x columns, which only the x part touches, are cleared by the epilogue
-//   with tcgen05.st before it hands the buffer back.
+//   h part (K = H): one N=192 MMA per k-step, packed W_hh rows ordered r|z|n, D column base 64 -> r, z, n_h
+//   x part (K = H): one N=192 MMA per k-step, packed W_ih rows ordered n|r|z, D column base  0 -> n_x, r, z
+//   Either part may run first (it overwrites its columns), the other accumulates.  The accumulate flag is per instruction,
+//   so the n_x and n_h columns, which only one part touches, are cleared by the epilogue with tcgen05.st before it hands the
+//   buffer back.
 // Linear tile = 256 streams x 128 outputs, one N=128 MMA per k-step.
 #pragma once
 
@@ -194,6 +195,7 @@ __global__ void pack_gru_weights_kernel(const __nv_bfloat16 *__restrict__ W, __n
 // host side
 struct TcModel {
     int H = 0, L = 0, Bp = 0;
+    int tcap = 1, e_ring = 1;      // step slots of feat / mask, slots of the encoder-output ring e
     const __nv_bfloat16 *enc_w = nullptr, *dec_w = nullptr, *wih[kMaxLayers] = {}, *whh[kMaxLayers] = {};
     const float *enc_b = nullptr, *dec_b = nullptr, *bih[kMaxLayers] = {}, *bhh[kMaxLayers] = {};
     __nv_bfloat16 *feat = nullptr, *e = nullptr, *hb[2] = {};

@@ -1,0 +1,150 @@
+"""The time-persistent mask-estimator launch (run on a B200: pytest -m gpu).
+
+A multi-frame call is taken in chunks: analysis of the chunk's frames, ONE fused kernel launch that walks the chunk's steps
+with per-(segment, stream tile) step counters, synthesis of the chunk.  The caller's serial frame loop is the reference's
+(/root/reference/demo/c/koala_demo_file.c:466-521; state carried inside the handle, /root/reference/include/pv_koala.h:65-80).
+Bit-for-bit checks against the same engine driven one frame per call; +-1 LSB checks against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import koala_b200 as kb
+from oracle import OracleBatch, OracleModel
+
+from conftest import synth_pcm
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+class env:
+    """Engine-creation knobs are read from the environment by Engine::create / fu_plan_create."""
+
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def frame_by_frame(model, n, pcm, precision="bf16"):
+    eng = kb.BatchKoala(n, model_path=model, precision=precision)
+    out = np.empty_like(pcm)
+    for t in range(pcm.shape[1]):
+        out[:, t] = eng.process(np.ascontiguousarray(pcm[:, t]))
+    h = [eng.debug_read(f"h{l}", (n, 512), np.float32) for l in range(2)]
+    eng.delete()
+    return out, h
+
+
+@pytest.mark.parametrize("n_streams,chunk", [(300, 8), (70, 5), (300, 64)])
+def test_chunked_call_is_bit_identical_to_frame_by_frame(library_path, random_model_path, n_streams, chunk):
+    """37 frames in one call (chunks of `chunk` frames = steps per fused launch) == 37 calls of one frame, output and state."""
+    import torch
+    frames = 37
+    pcm = synth_pcm(n_streams, frames, seed=700 + n_streams)
+    ref, ref_h = frame_by_frame(random_model_path, n_streams, pcm)
+    with env(KOALA_CHUNK_FRAMES=chunk):
+        eng = kb.BatchKoala(n_streams, model_path=random_model_path, precision="bf16")
+    assert eng.chunk_frames == chunk
+    # host buffers, stream-major
+    out = eng.process(pcm)
+    assert (out == ref).all()
+    for l in range(2):
+        assert (eng.debug_read(f"h{l}", (n_streams, 512), np.float32) == ref_h[l]).all()
+    launches = eng.kernel_launches
+    # device buffers, both layouts, after a reset
+    eng.reset()
+    d = torch.from_numpy(pcm).cuda()
+    out_d = eng.process(d).cpu().numpy()
+    assert eng.kernel_launches - launches == 3 * ((frames + chunk - 1) // chunk)      # analysis, fused mask estimator, synthesis per chunk
+    assert (out_d == ref).all()
+    eng.reset()
+    d_tm = torch.from_numpy(np.ascontiguousarray(pcm.transpose(1, 0, 2))).cuda()
+    out_tm = eng.process(d_tm, time_major=True).cpu().numpy().transpose(1, 0, 2)
+    assert (out_tm == ref).all()
+    # in place: the caller's output buffer may be its input buffer
+    eng.reset()
+    d2 = torch.from_numpy(pcm).cuda()
+    eng.process(d2, out=d2)
+    assert (d2.cpu().numpy() == ref).all()
+    eng.delete()
+
+
+def test_chunked_call_against_oracle_small_batch(library_path, random_model_path):
+    """configs[4]-shaped: 128 streams, 64-frame calls with the state carried across calls; +-1 LSB of the oracle."""
+    n, frames, calls = 128, 64, 3
+    pcm = synth_pcm(n, frames * calls, seed=41)
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    out = np.concatenate([eng.process(np.ascontiguousarray(pcm[:, c * frames:(c + 1) * frames])) for c in range(calls)], axis=1)
+    ob = OracleBatch(OracleModel(random_model_path), n, "bf16")
+    ref = ob.process(pcm, threads=8)
+    diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1, diff.max()
+    for l in range(2):
+        h = eng.debug_read(f"h{l}", (n, 512), np.float32)
+        np.testing.assert_allclose(h, np.stack([ob.stream(s).h[l] for s in range(n)]), atol=1e-3)
+    eng.delete()
+
+
+def test_few_clusters_do_not_deadlock(library_path, random_model_path):
+    """The dependency waits are only ever for tiles earlier in the list, so any grid size must finish and give the same bits:
+    3 CTA pairs walk 24 steps of 300 streams (every wait is then for a tile of the same or a neighbouring pair)."""
+    n, frames = 300, 24
+    pcm = synth_pcm(n, frames, seed=77)
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    ref = eng.process(pcm)
+    eng.delete()
+    for clusters in (1, 3):
+        with env(KOALA_FU_CLUSTERS=clusters):
+            eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+        out = eng.process(pcm)
+        assert (out == ref).all(), clusters
+        eng.delete()
+
+
+def test_both_part_orders_agree_with_the_oracle(library_path, random_model_path):
+    """x part first (small batches) and h part first (big batches) differ only in fp32 summation order."""
+    n, frames = 130, 20
+    pcm = synth_pcm(n, frames, seed=5)
+    ref = OracleBatch(OracleModel(random_model_path), n, "bf16").process(pcm, threads=8)
+    for order in (0, 1):
+        with env(KOALA_FU_XFIRST=order):
+            eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+        out = eng.process(pcm)
+        assert np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= 1, order
+        eng.delete()
+
+
+def test_full_size_chunk_boundary(library_path, random_model_path):
+    """8192 streams x 20 frames in one call (default chunk = 16 frames: one boundary): replicas bit-identical, silent streams
+    silent, equal to the one-frame-per-call drive of a second engine, oracle spot check."""
+    import torch
+    n, frames = 8192, 20
+    base = synth_pcm(64, frames, seed=19)
+    pcm = np.tile(base, (n // 64, 1, 1))
+    pcm[5::64] = 0
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    assert eng.chunk_frames >= 2
+    d_in = torch.from_numpy(np.ascontiguousarray(pcm.transpose(1, 0, 2))).cuda()       # time-major
+    out = eng.process(d_in, time_major=True).cpu().numpy().transpose(1, 0, 2)
+    eng.delete()
+    assert (out.reshape(n // 64, 64, frames, 256) == out[:64][None]).all()
+    assert (out[5::64] == 0).all()
+    eng1 = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    one = np.empty_like(pcm)
+    for t in range(frames):
+        one[:, t] = eng1.process(d_in[t]).cpu().numpy()
+    eng1.delete()
+    assert (one == out).all()
+    pick = [0, 1, 2, 3, 6, 7, 17, 63, 4096 + 9, 8191]
+    ref = OracleBatch(OracleModel(random_model_path), len(pick), "bf16").process(np.ascontiguousarray(pcm[pick]), threads=8)
+    assert np.abs(out[pick].astype(np.int32) - ref.astype(np.int32)).max() <= 1
