@@ -300,6 +300,7 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             if (const char *e = getenv("KOALA_CHUNK_FRAMES")) cap = std::max(1, std::min(256, atoi(e)));
             p->tcap = cap;
             p->e_ring = std::min(cap, kFuSlots);
+            if (const char *e = getenv("KOALA_E_RING")) p->e_ring = std::max(1, std::min(p->e_ring, atoi(e)));
         }
         const size_t T = p->tcap;
         KCHECK(dev_alloc(p->allocs, &p->spec, T * Bp * kNfft));

@@ -8,9 +8,12 @@
 // ~8 k) on every frame, and at small stream counts is nothing but dependency latency (profiles/r01_step_summary.md).  Here a
 // launch takes `steps` consecutive frames.  The building blocks are those of tcgen05_common.cuh (bf16 operands staged by TMA
 // into 128B-swizzled shared memory, tcgen05.mma.cta_group::2 accumulating fp32 in TMEM, gate math fused into the epilogue);
-// this file is the schedule: one global list of pair tiles
-//     step 0: [encoder | GRU layer 0 | ... | GRU layer L-1 | decoder],  step 1: [...],  ...      each segment m-major,
-// walked round-robin by persistent CTA pairs (2-CTA clusters on all 148 SMs).  Dependencies are per (segment, 256-stream m
+// this file is the schedule: one global list of pair tiles, period p = 0 .. steps + 1, each segment m-major,
+//     period p: [GRU layer 0 of step p-1 | decoder of step p-2 | encoder of step p | GRU layer 1 of step p-1 | ... ]
+// (tiles whose step falls outside the launch are skipped), walked round-robin by persistent CTA pairs (2-CTA clusters on all
+// 148 SMs).  The encoder runs a step ahead and the decoder a step behind so that in the steady state every tile's producers
+// are at least four rounds of the grid back in the list: with [enc | GRU 0 | GRU 1 | dec] per step the first GRU tiles of a
+// step waited ~6 k cycles for encoder tiles issued just before them and the last decoder tiles a whole GRU tile (r02c trace).  Dependencies are per (segment, 256-stream m
 // tile, step slot) COUNTERS in global memory that are never reset: every CTA of a tile of global step g (steps since the
 // engine was created, 0-based) adds 1 to slot g % 4 of its row once the tile's output stores have completed, so "segment s
 // has finished step g for m tile m" reads counter[s][m][g % 4] >= (g / 4 + 1) * (CTAs per m tile of that segment).  (One
@@ -75,11 +78,11 @@ struct FuSeg {
     int mode;                 // kTcEnc | kTcGru | kTcDec
     int n_tiles;              // pair tiles along n
     int kb_per_part, parts;   // k-blocks of 64 per operand part; GRU has two parts (x and h)
-    int tile_begin;           // index of the segment's first tile inside one step's list
+    int step_delta;           // a tile of this segment in period p belongs to step p - 1 + step_delta (encoder +1, decoder -1)
     int x_first;              // GRU: the x part runs before the h part
     unsigned inc;             // what one step adds to this segment's counter of an m tile (2 CTAs per n tile)
     const float *bias0, *bias1;
-    const __nv_bfloat16 *a1[2];   // GRU: bf16 h(t-1) operand [Bp][H] by state parity, for the L2 prefetch of the next tile
+    int a0_rows, a1_rows, b_rows;   // KOALA_FU_FAKE_KB timing experiment: rows of the operand matrices
 };
 struct FuArgs {
     int nseg, num_m_tiles, tiles_per_step, total_tiles, H, Bp;
@@ -90,6 +93,9 @@ struct FuArgs {
     unsigned *counters;       // [nseg][num_m_tiles][kFuSlots]
     const CUtensorMap *maps;  // [2 parities][nseg][kFuMapsPerSeg], global memory
     long long *trace;
+    int trace_skip;           // trace builds: first tile (of each pair's own sequence) that is recorded
+    int pos_seg[kFuMaxSegs];          // list order inside a period: segment at position i ...
+    int pos_begin[kFuMaxSegs + 1];    // ... and the index of its first tile
     FuSeg seg[kFuMaxSegs];
 };
 
@@ -121,23 +127,31 @@ __device__ __forceinline__ void fu_wait_counter(const unsigned *ctr, unsigned ta
 
 // position of one pair tile in the global list
 struct FuTile {
-    int t, s, m, n;           // step inside the launch, segment, m tile, n tile
+    int t, s, m, n;           // step inside the launch, segment (-1: list position without a tile in this launch), m tile, n tile
     int par;                  // parity of the state buffers that hold h(t-1) of this step
     long long g;              // global step index (0-based): epoch0 + t
 };
 __device__ __forceinline__ FuTile fu_decode(const FuArgs &a, int g) {
     FuTile r;
-    r.t = g / a.tiles_per_step;
-    const int local = g - r.t * a.tiles_per_step;
-    int s = 0;
-    while (s + 1 < a.nseg && local >= a.seg[s + 1].tile_begin) ++s;
-    const int in_seg = local - a.seg[s].tile_begin, nt = a.seg[s].n_tiles;
-    r.s = s;
+    const int p = g / a.tiles_per_step, local = g - p * a.tiles_per_step;
+    int i = 0;
+    while (i + 1 < a.nseg && local >= a.pos_begin[i + 1]) ++i;
+    const int s = a.pos_seg[i], in_seg = local - a.pos_begin[i], nt = a.seg[s].n_tiles;
+    r.t = p - 1 + a.seg[s].step_delta;
+    r.s = (r.t >= 0 && r.t < a.steps) ? s : -1;
     r.m = in_seg / nt;
     r.n = in_seg - r.m * nt;
     r.par = (a.cur0 + r.t) & 1;
     r.g = a.epoch0 + r.t;
     return r;
+}
+// the pair's next tile at or after list position g (stride = pairs in the grid); false when the list is exhausted
+__device__ __forceinline__ bool fu_next(const FuArgs &a, int &g, int stride, FuTile &t) {
+    for (; g < a.total_tiles; g += stride) {
+        t = fu_decode(a, g);
+        if (t.s >= 0) return true;
+    }
+    return false;
 }
 // "segment s has finished global step g for m tile m": the counter and the value it has reached by then.  False: nothing to
 // wait for (before the engine's first step).
@@ -158,17 +172,25 @@ __device__ __forceinline__ bool fu_dep_h(const FuArgs &a, const FuTile &t, const
     return a.seg[t.s].mode == kTcGru && fu_done_ctr(a, t.s, t.m, t.g - 1, ctr, target);
 }
 // (w): the readers of the buffer this tile's stores overwrite must be done
-__device__ __forceinline__ void fu_wait_war(const FuArgs &a, const FuTile &t) {
+__device__ __forceinline__ bool fu_dep_w(const FuArgs &a, const FuTile &t, const unsigned *&ctr, unsigned &target) {
     const FuSeg &sg = a.seg[t.s];
-    const unsigned *ctr = nullptr;
-    unsigned target = 0;
-    bool need = false;
     if (sg.mode == kTcEnc)         // ring slot g % ring was read by GRU layer 0 of step g - ring
-        need = fu_done_ctr(a, 1, t.m, t.g - a.e_ring, ctr, target);
-    else if (sg.mode == kTcGru)    // the bf16 copy this step writes held h(g-2), read as the x operand by the next segment at step g-2
-        need = fu_done_ctr(a, t.s + 1, t.m, t.g - 2, ctr, target);
-    if (need) fu_wait_counter(ctr, target);
+        return fu_done_ctr(a, 1, t.m, t.g - a.e_ring, ctr, target);
+    if (sg.mode == kTcGru)         // the bf16 copy this step writes held h(g-2), read as the x operand by the next segment at step g-2
+        return fu_done_ctr(a, t.s + 1, t.m, t.g - 2, ctr, target);
+    return false;
 }
+// A dependency sampled ahead of time: the relaxed load is issued when the tile is decoded and only looked at when the tile
+// is reached, so its L2 round trip (~1 k cycles under load) stays off the critical path; if it did not hold yet, poll.
+struct FuDep {
+    const unsigned *ctr;
+    unsigned target, seen;
+    __device__ __forceinline__ void none() { ctr = nullptr; target = 0; seen = 0; }
+    __device__ __forceinline__ void sample() { if (ctr) seen = ld_relaxed_gpu(ctr); }
+    __device__ __forceinline__ bool holds() { return ctr == nullptr || (int) (seen - target) >= 0; }
+    __device__ __forceinline__ bool poll() { sample(); return holds(); }
+    __device__ __forceinline__ void wait() { if (!holds()) { fu_wait_counter(ctr, target); seen = target; } }
+};
 
 __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads, 1) tc_fused_kernel(const __grid_constant__ FuArgs args) {
     constexpr int kStages = kFuStages, kStageBytes = kFuStageBytes;
@@ -196,16 +218,16 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
     constexpr uint16_t pair_mask = 3;
     [[maybe_unused]] long long *trace = (args.trace != nullptr && blockIdx.x < 2) ? args.trace + blockIdx.x * 1024 : nullptr;
 #ifdef KOALA_FU_TRACE      // clock64 timeline of cluster 0 (tools/gpu_trace.py builds this variant); compiled out of the product
-#define KTRACE(slot) do { if (trace && (slot) < 1020) trace[(slot)] = clock64(); } while (0)
-#define KTRACE_HDR(slot) do { if (trace) trace[(slot)] = clock64(); } while (0)
+#define KTRACE(tile, slot) do { const int ti__ = (tile) - args.trace_skip; if (trace && ti__ >= 0 && ti__ < 21) trace[ti__ * 48 + (slot)] = clock64(); } while (0)   /* 21 tiles x 48 slots = 1008; 1012..1015 globaltimer, 1020..1023 clock64 of the header events */
+#define KTRACE_HDR(slot) do { if (trace) { trace[(slot)] = clock64(); unsigned long long ns__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns__)); trace[(slot) - 8] = (long long) ns__; } } while (0)
 #else
-#define KTRACE(slot) do { } while (0)
+#define KTRACE(tile, slot) do { } while (0)
 #define KTRACE_HDR(slot) do { } while (0)
 #endif
     if (threadIdx.x == 0) KTRACE_HDR(1020);
     pdl_launch_dependents();
     const int cluster_id = blockIdx.x / kFuCluster, num_clusters = gridDim.x / kFuCluster;
-    const int total = args.total_tiles;
+    const int total = args.total_tiles;   // list positions (valid or not)
 
     if (warp == 0) {
         for (int i = lane; i < 2 * args.nseg * kFuMapsPerSeg; i += 32) prefetch_tmap(args.maps + i);
@@ -248,8 +270,10 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         int pit = 0;
         unsigned seen_x = 0, seen_h = 0;    // the next tile's dependency counters, sampled one tile early (hides the L2 round trip)
         bool have_seen = false;
-        for (int g = cluster_id; g < total; g += num_clusters, ++pit) {
-            const FuTile t = fu_decode(args, g);
+        FuTile t, t1;
+        int g = cluster_id, g1 = 0;
+        bool have = fu_next(args, g, num_clusters, t), have1 = false;
+        for (; have; g = g1, t = t1, have = have1, ++pit) {
             const FuSeg &sg = args.seg[t.s];
             const CUtensorMap *maps = args.maps + (size_t) (t.par * args.nseg + t.s) * kFuMapsPerSeg;
             const bool gru = sg.mode == kTcGru;
@@ -264,7 +288,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             const unsigned my_seen_x = seen_x, my_seen_h = seen_h;
             const bool my_have = have_seen;
             have_seen = false;
-            if (warp == 0 && lane == 0) KTRACE(pit * 48 + 0);
+            if (warp == 0 && lane == 0) KTRACE(pit, 0);
             for (int kb = par; kb < num_kb; kb += 2) {
                 const int part = kb >= kbp ? 1 : 0;
                 const bool hp = part == hpart;
@@ -273,36 +297,39 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                     unsigned target = 0;
                     const bool need = hp ? fu_dep_h(args, t, ctr, target) : fu_dep_x(args, t, ctr, target);
                     if (need && !(my_have && (int) ((hp ? my_seen_h : my_seen_x) - target) >= 0)) fu_wait_counter(ctr, target);
-                    if (warp == 0 && lane == 0) KTRACE(pit * 48 + 12 + part);
+                    if (warp == 0 && lane == 0) KTRACE(pit, 12 + part);
                 }
                 mbar_wait(&empty_bar[stage], phase ^ 1);     // slot free in both CTAs of the pair
-                if (is_a && lane == 0) KTRACE(pit * 48 + 16 + kb);
+                if (is_a && lane == 0) KTRACE(pit, 16 + kb);
                 const bool elected = elect_one();
                 if (elected && is_a && rank == 0) mbar_expect_tx(&full_bar[stage], pair_tx);
                 const uint32_t full_leader = map_to_cta(&full_bar[stage], leader);
                 uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kTcABytes;
                 const int kc = (kb - part * kbp) * kTcBlockK;
                 if (!elected) {
+#ifdef KOALA_FU_FAKE_KB    // timing experiment: the same bytes as contiguous [rows][64] boxes of a K-blocked view of the same memory (wrong data)
+                } else if (is_a) {
+                    tma_load_2d_pair(maps + (hp ? kMapA1 : kMapA0), full_leader, sa, 0, (kc / kTcBlockK) * (hp ? sg.a1_rows : sg.a0_rows) + (hp ? a1_row : a0_row));
+                } else {
+                    tma_load_2d_pair(maps + (hp ? kMapB1 : kMapB0), full_leader, sb, 0, (kc / kTcBlockK) * sg.b_rows + t.n * 2 * brows + (int) rank * brows);
+#else
                 } else if (is_a) {
                     tma_load_2d_pair(maps + (hp ? kMapA1 : kMapA0), full_leader, sa, kc, hp ? a1_row : a0_row);
                 } else {
                     tma_load_2d_pair(maps + (hp ? kMapB1 : kMapB0), full_leader, sb, kc, t.n * 2 * brows + (int) rank * brows);
+#endif
                 }
                 __syncwarp();
-                if (kb == par && (is_a || warp == 4)) {
-                    const int g1 = g + num_clusters;
-                    if (g1 < total) {
-                        const FuTile t1 = fu_decode(args, g1);
+                if (kb == par) {         // my first load of the tile is on its way: decode the pair's next tile behind it
+                    g1 = g + num_clusters;
+                    have1 = fu_next(args, g1, num_clusters, t1);
+                    if (have1) {
                         if (is_a) {
                             const unsigned *ctr = nullptr;
                             unsigned target = 0;
                             if (fu_dep_x(args, t1, ctr, target)) seen_x = ld_relaxed_gpu(ctr);
                             if (fu_dep_h(args, t1, ctr, target)) seen_h = ld_relaxed_gpu(ctr);
                             have_seen = true;
-                        } else if (args.seg[t1.s].mode == kTcGru && elect_one()) {
-                            // h(t-1) operands may have to come from HBM (written a whole step ago): my 128 rows of the next
-                            // tile's operand are one contiguous range; request it into L2 now, a whole mainloop ahead
-                            prefetch_l2(args.seg[t1.s].a1[t1.par] + (size_t) (t1.m * kTcPairM + arow) * args.H, (uint32_t) (kTcBlockM * args.H * 2));
                         }
                     }
                     __syncwarp();
@@ -310,7 +337,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 stage += 2;
                 if (stage >= kStages) { stage -= kStages; phase ^= 1; }
             }
-            if (warp == 0 && lane == 0) KTRACE(pit * 48 + 1);
+            if (warp == 0 && lane == 0) KTRACE(pit, 1);
         }
     } else if (warp == 2) {
         // ===================================================== MMA issuer (one thread of the leader CTA drives both SMs)
@@ -318,17 +345,23 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             int it = 0;
             unsigned kb_total = 0;           // k-blocks issued so far: every lane derives the pipeline position from it
             const uint64_t adesc0 = make_sw128_desc(smem_u32(smem)), bdesc0 = make_sw128_desc(smem_u32(smem) + kTcABytes);
-            for (int g = cluster_id; g < total; g += num_clusters, ++it) {
-                const FuTile t = fu_decode(args, g);
+            FuTile t, t_next;
+            int g = cluster_id;
+            bool have = fu_next(args, g, num_clusters, t);
+            for (; have; ++it) {
                 const FuSeg &sg = args.seg[t.s];
                 const bool gru = sg.mode == kTcGru;
                 const int num_kb = sg.kb_per_part * sg.parts, kbp = sg.kb_per_part;
                 const uint32_t idesc = gru ? make_idesc(256, kGruRows) : make_idesc(256, kFuLinN);
                 const int hpart = gru ? (sg.x_first ? 1 : 0) : -1;
                 const int ab = it & 1, aphase = (it >> 1) & 1;
+                // the next tile is decoded here, in front of this tile's barrier waits, which absorb it: decoded after the k
+                // loop it was ~600 idle cycles of the tensor pipe per tile (r02d trace)
+                g += num_clusters;
+                have = fu_next(args, g, num_clusters, t_next);
                 mbar_wait(&tmem_empty[ab], aphase);      // both CTAs' epilogues have released (and cleared) this buffer
                 tc_fence_after();
-                if (lane == 0) KTRACE(it * 48 + 2);
+                if (lane == 0) KTRACE(it, 2);
                 const uint32_t d = tmem_base + ab * kTcAccCols;
                 // The whole k loop runs in ONE elected lane: every instruction between two k-blocks (barrier test, descriptor
                 // arithmetic, moves into uniform registers) is serial latency of this thread and shows up one-for-one in the
@@ -345,7 +378,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                         for (int kb = 0; kb < kbp; ++kb) {
                             mbar_wait(&full_bar[stage], phase);
                             tc_fence_after();
-                            KTRACE(it * 48 + 32 + part * kbp + kb);
+                            KTRACE(it, 32 + part * kbp + kb);
                             const uint64_t so = (uint64_t) ((stage * kStageBytes) >> 4);
 #pragma unroll
                             for (int k = 0; k < kTcBlockK / 16; ++k)    // +32 B per 16-element k-step
@@ -357,7 +390,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                     umma_commit_pair(&tmem_full[ab], pair_mask);
                 }
                 __syncwarp();
-                if (lane == 0) KTRACE(it * 48 + 3);
+                if (lane == 0) KTRACE(it, 3);
+                t = t_next;
             }
         }
     } else if (warp == kTcStateWarp) {
@@ -374,14 +408,21 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             struct PassIter {
                 int g, c;
                 FuTile t;
+                FuDep h, w;      // the tile's (h) and (w) dependencies, sampled when the iterator reaches the tile
             };
             auto start = [&](PassIter &p, int g) {           // first pass of the pair's next GRU tile at or after g
-                for (; g < total; g += num_clusters) {
-                    p.t = fu_decode(args, g);
+                for (; fu_next(args, g, num_clusters, p.t); g += num_clusters)
                     if (args.seg[p.t.s].mode == kTcGru) break;
-                }
                 p.g = g;
                 p.c = 0;
+                p.h.none();
+                p.w.none();
+                if (g < total) {
+                    fu_dep_h(args, p.t, p.h.ctr, p.h.target);
+                    fu_dep_w(args, p.t, p.w.ctr, p.w.target);
+                    p.h.sample();
+                    p.w.sample();
+                }
             };
             auto advance = [&](PassIter &p) {
                 if (++p.c == 2) start(p, p.g + num_clusters);
@@ -392,11 +433,9 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             unsigned armed = 0, pc = 0;      // passes requested / stored so far; pass q uses staging buffer q & 1
             auto try_arm = [&](bool block) {
                 if (ahead.g >= total || armed >= pc + 2) return;          // nothing left, or the buffer still holds an unstored pass
-                const unsigned *ctr = nullptr;
-                unsigned target = 0;
-                if (fu_dep_h(args, ahead.t, ctr, target) && (int) (ld_relaxed_gpu(ctr) - target) < 0) {
+                if (!ahead.h.holds() && !ahead.h.poll()) {
                     if (!block) return;
-                    fu_wait_counter(ctr, target);
+                    ahead.h.wait();
                 }
                 const int buf = (int) (armed & 1);
                 mbar_expect_tx(&box_ready[buf], kFuBoxF32);
@@ -413,11 +452,11 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 const CUtensorMap *maps = args.maps + (size_t) (cur.t.par * args.nseg + cur.t.s) * kFuMapsPerSeg;
                 const int row = cur.t.m * kTcPairM + row0, col = cur.t.n * kGruUnits + 32 * cur.c;
                 mbar_wait(&staged[buf], (pc >> 1) & 1);
-                if (cur.c == 0) fu_wait_war(args, cur.t);
+                if (cur.c == 0) cur.w.wait();
                 tma_store_2d(maps + kMapHn, s_f32 + buf * kFuBoxF32, col, row);
                 tma_store_2d(maps + kMapHb, s_b16 + buf * kFuBoxB16, col, row);
                 bulk_commit();
-                KTRACE(it * 48 + 9 + (cur.c & 1) * 2);
+                KTRACE((cur.g - cluster_id) / num_clusters, 9 + (cur.c & 1) * 2);
                 bulk_wait_read();                            // the stores have read buffer `buf`
                 ++pc;
                 if (cur.c == 1) {
@@ -441,16 +480,20 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         if (elect_one()) {
             const int row0 = (int) rank * kTcBlockM;
             unsigned n16 = 0, n8 = 0;
-            for (int g = cluster_id; g < total; g += num_clusters) {
-                const FuTile t = fu_decode(args, g);
+            FuTile t;
+            for (int g = cluster_id; fu_next(args, g, num_clusters, t); g += num_clusters) {
                 const FuSeg &sg = args.seg[t.s];
                 if (sg.mode == kTcGru) continue;
                 const CUtensorMap *map = args.maps + (size_t) (t.par * args.nseg + t.s) * kFuMapsPerSeg + kMapHn;
                 const int col = t.n * kFuLinN;
+                FuDep w;
+                w.none();
+                fu_dep_w(args, t, w.ctr, w.target);
+                w.sample();                        // looked at after the wait for the staged tile
                 if (sg.mode == kTcEnc) {           // two boxes of 64 bf16 columns into ring slot G % ring
                     const int row = t.m * kTcPairM + row0 + (int) (t.g % args.e_ring) * args.Bp;
                     mbar_wait(lin_staged16, n16++ & 1);
-                    fu_wait_war(args, t);
+                    w.wait();
                     tma_store_2d(map, s_lin, col, row);
                     tma_store_2d(map, s_lin + kFuBoxF32, col + 64, row);
                     bulk_commit();
@@ -502,8 +545,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         constexpr float kL2e = 1.4426950408889634f;
         unsigned pc = 0, lf = 0;       // GRU passes / linear rounds so far: staging buffer and barrier phase
         int it = 0;
-        for (int g = cluster_id; g < total; g += num_clusters, ++it) {
-            const FuTile t = fu_decode(args, g);
+        FuTile t;
+        for (int g = cluster_id; fu_next(args, g, num_clusters, t); g += num_clusters, ++it) {
             const FuSeg &sg = args.seg[t.s];
             const int mode = sg.mode, n = t.n;
             const int ab = it & 1, aphase = (it >> 1) & 1;
@@ -522,10 +565,10 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 if (te < kFuLinN) sb[te] = __ldg(sg.bias0 + n * kFuLinN + te);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");   // the epilogue threads only
-            if (te == 0) KTRACE(it * 48 + 4);
+            if (te == 0) KTRACE(it, 4);
             mbar_wait(&tmem_full[ab], aphase);
             tc_fence_after();
-            if (te == 0) KTRACE(it * 48 + 5);
+            if (te == 0) KTRACE(it, 5);
             const uint32_t t0 = lane_base + ab * kTcAccCols;
             if (mode != kTcGru) {
                 // linear tile: my warp owns 32 of the 128 outputs (columns part * 32 ..), one row per thread.  The accumulator
@@ -540,7 +583,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 tmem_zero8(t0 + part * 16 + 8);
                 tmem_st_wait();
                 tc_fence_before();
-                if (te == 0) KTRACE(it * 48 + 6);
+                if (te == 0) KTRACE(it, 6);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(empty_leader[ab]);
 #pragma unroll
@@ -582,6 +625,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 tmem_ld8(t0 + 64 + cu, ar);
                 tmem_ld8(t0 + 128 + cu, az);
                 tmem_ld8(t0 + 192 + cu, anh);
+                if (te == 0) KTRACE(it, 14 + c);
                 mbar_wait(&box_ready[buf], (pc >> 1) & 1);   // h(t-1) of this pass has landed
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -589,7 +633,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                     hp[4 * q] = v.x; hp[4 * q + 1] = v.y; hp[4 * q + 2] = v.z; hp[4 * q + 3] = v.w;
                 }
                 tmem_ld_wait();
-                if (te == 0) KTRACE(it * 48 + 8 + c * 2);
+                if (te == 0) KTRACE(it, 8 + c * 2);
                 tmem_zero8(t0 + cu);                         // the n columns only one operand part touches must be zero when the
                 tmem_zero8(t0 + 3 * kGruUnits + cu);         // next GRU tile's second part accumulates into them
 #pragma unroll
@@ -608,7 +652,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 if (c == 1) {                                // last TMEM access of this tile: hand the buffer back
                     tmem_st_wait();
                     tc_fence_before();
-                    if (te == 0) KTRACE(it * 48 + 6);
+                    if (te == 0) KTRACE(it, 6);
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(empty_leader[ab]);
                 }
@@ -691,8 +735,10 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     ok = ok && cudaMalloc((void **) &f->counters, (size_t) nseg * mt * kFuSlots * sizeof(unsigned)) == cudaSuccess &&
               cudaMemset(f->counters, 0, (size_t) nseg * mt * kFuSlots * sizeof(unsigned)) == cudaSuccess;
+    int trace_skip = 0;
     if (const char *tr = getenv("KOALA_FU_TRACE_BUF")) {
         if (tr[0] == '1' && cudaMalloc((void **) &f->trace, 2048 * sizeof(long long)) == cudaSuccess) cudaMemset(f->trace, 0, 2048 * sizeof(long long));
+        if (const char *sk = getenv("KOALA_FU_TRACE_SKIP")) trace_skip = atoi(sk);
     }
     ok = ok && cudaFuncSetAttribute(tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes) == cudaSuccess;
     int resident_pairs = f->num_sms / kFuCluster;      // CTA pairs the device can hold at once
@@ -714,26 +760,34 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
     std::vector<CUtensorMap> maps((size_t) 2 * nseg * kFuMapsPerSeg);
     FuArgs &a = f->args;
     memset(&a, 0, sizeof(a));
-    a.nseg = nseg; a.num_m_tiles = mt; a.H = m.H; a.Bp = m.Bp; a.e_ring = m.e_ring; a.counters = f->counters; a.trace = f->trace;
-    int tile = 0;
+    a.nseg = nseg; a.num_m_tiles = mt; a.H = m.H; a.Bp = m.Bp; a.e_ring = m.e_ring; a.counters = f->counters; a.trace = f->trace; a.trace_skip = trace_skip;
     for (int s = 0; s < nseg; s++) {
         FuSeg &sg = a.seg[s];
-        sg.tile_begin = tile;
         if (s == 0) {                                  // encoder: e = relu(feat W_enc^T + b)
-            sg.mode = kTcEnc; sg.n_tiles = m.H / kFuLinN; sg.kb_per_part = kBins / kTcBlockK; sg.parts = 1;
+            sg.mode = kTcEnc; sg.n_tiles = m.H / kFuLinN; sg.kb_per_part = kBins / kTcBlockK; sg.parts = 1; sg.step_delta = 1;
             sg.bias0 = m.enc_b;
         } else if (s == nseg - 1) {                    // decoder: mask = sigmoid(h_{L-1}(t) W_dec^T + b)
-            sg.mode = kTcDec; sg.n_tiles = kBins / kFuLinN; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 1;
+            sg.mode = kTcDec; sg.n_tiles = kBins / kFuLinN; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 1; sg.step_delta = -1;
             sg.bias0 = m.dec_b;
         } else {                                       // GRU layer l
             const size_t l = s - 1;
-            sg.mode = kTcGru; sg.n_tiles = m.H / kGruUnits; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 2;
+            sg.mode = kTcGru; sg.n_tiles = m.H / kGruUnits; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 2; sg.step_delta = 0;
             sg.bias0 = m.bih[l]; sg.bias1 = m.bhh[l];
-            for (int par = 0; par < 2; par++) sg.a1[par] = m.hb[par] + l * LBH;
         }
         sg.inc = (unsigned) (2 * sg.n_tiles);          // the rows of an m tile are written by both CTAs of every n tile
-        tile += mt * sg.n_tiles;
     }
+    // list order inside a period: GRU layer 0, decoder (a step behind), encoder (a step ahead), GRU layers 1..
+    int tile = 0, npos = 0;
+    auto place = [&](int s) {
+        a.pos_seg[npos] = s;
+        a.pos_begin[npos++] = tile;
+        tile += mt * a.seg[s].n_tiles;
+    };
+    place(1);
+    place(nseg - 1);
+    place(0);
+    for (int s = 2; s < nseg - 1; s++) place(s);
+    a.pos_begin[npos] = tile;
     a.tiles_per_step = tile;
     // small batches are bound by the latency of the recurrence GRU_l(t-1) -> GRU_l(t): run the x part (whose operands exist
     // earlier) first, so that only the h half of the k loop follows the wait.  KOALA_FU_XFIRST=0/1 overrides.
@@ -747,6 +801,13 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
             bool used[kFuMapsPerSeg] = {};
             auto put = [&](int k, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool f32 = false, bool plain32 = false) {
                 used[k] = true;
+#ifdef KOALA_FU_FAKE_KB
+                if (k == kMapA0 || k == kMapA1 || k == kMapB0 || k == kMapB1) {
+                    (k == kMapA0 ? a.seg[s].a0_rows : k == kMapA1 ? a.seg[s].a1_rows : a.seg[s].b_rows) = (int) rows;
+                    rows *= cols / kTcBlockK;
+                    cols = kTcBlockK;
+                }
+#endif
                 ok = ok && encode_2d(fn, &mp[k], base, rows, cols, box_rows, f32, plain32);
             };
             if (s == 0) {
@@ -792,8 +853,8 @@ static int fu_masknet_steps(FuPlan *f, int cur, int steps, cudaStream_t st) {
     a.steps = steps;
     a.cur0 = cur;
     a.epoch0 = f->epoch;
-    a.total_tiles = steps * a.tiles_per_step;
-    const int clusters = a.total_tiles < f->max_clusters ? a.total_tiles : f->max_clusters;
+    a.total_tiles = (steps + 2) * a.tiles_per_step;       // periods 0 .. steps + 1 (the first holds only encoder tiles, the last only decoder tiles)
+    const int clusters = steps * a.tiles_per_step < f->max_clusters ? steps * a.tiles_per_step : f->max_clusters;
     // the epoch only advances with a launch that was accepted: the counters then stand at epoch * (increments per step), which
     // is what the next launch waits for (the caller reports the launch error through cudaGetLastError)
     if (launch_pdl(true, tc_fused_kernel, dim3((unsigned) (kFuCluster * clusters)), dim3(kFuThreads), (size_t) kFuSmemBytes, st, a) == cudaSuccess)

@@ -1,4 +1,4 @@
-"""Time one step of the bf16 path with a given build of the library (tuning variants built by
+"""Time the steps of the bf16 path with a given build of the library (tuning variants built by
 `python -m koala_b200._build -DNAME=VALUE -o<path>`): python tools/variant_bench.py <lib.so> [streams] [steps]."""
 import os, sys
 import numpy as np
@@ -17,9 +17,10 @@ pcm = torch.from_numpy((np.random.default_rng(0).standard_normal((ring, n, 256))
 out = torch.empty_like(pcm)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 lib, h = eng._library, eng._handle
+fpc = int(os.environ.get("FPC", "16"))        # frames per call (bench.py's headline: 16); the timed unit below is one such call
 def step(i):
-    off = (i % ring) * n * 512
-    rc = lib.pv_koala_batch_process_async(h, pcm.data_ptr() + off, out.data_ptr() + off, 1, 256, c_void_p(st.cuda_stream))
+    off = ((i * fpc) % ring) * n * 512
+    rc = lib.pv_koala_batch_process_async_strided(h, pcm.data_ptr() + off, out.data_ptr() + off, fpc, 256, n * 256, c_void_p(st.cuda_stream))
     assert rc == 0
 for i in range(20): step(i)
 torch.cuda.synchronize()
@@ -27,8 +28,8 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(st)
 for i in range(steps): step(i)
 e1.record(st); torch.cuda.synchronize()
-us = e0.elapsed_time(e1) / steps * 1e3
+us = e0.elapsed_time(e1) / (steps * fpc) * 1e3
 eng.profile(True)
 for i in range(100): step(i)
 prof = eng.profile_read(); eng.profile(False)
-print(f"{os.path.basename(lib_path):40s} step {us:7.2f} us | " + " ".join(f"{k} {v[0] / max(v[1], 1) * 1e3:6.2f}" for k, v in prof.items() if v[1]))
+print(f"{os.path.basename(lib_path):40s} {fpc} frames/call: step {us:7.2f} us | per step: " + " ".join(f"{k} {v[0] / (100 * fpc) * 1e3:6.2f}" for k, v in prof.items() if v[1]))
