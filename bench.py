@@ -38,7 +38,8 @@ WORKLOADS = {
     "cfg3_4096_bf16": dict(streams=4096, precision="bf16", frames_per_call=32, time_major=True,
                            desc="BASELINE configs[2]: 4096 concurrent streams, 1xB200, bf16 tensor-core mask-estimator GEMMs"),
     "cfg2_256_fp32": dict(streams=256, precision="fp32", frames_per_call=64,
-                          desc="BASELINE configs[1]: 256 concurrent streams, 1xB200, fp32 mask path, fed 64 frames per process() call"),
+                          desc="BASELINE configs[1]: 256 concurrent streams, 1xB200, fp32 mask path (tcgen05 with every activation split into "
+                               "three bf16 planes, fp32 accumulation), fed 64 frames per process() call"),
     "cfg5_128_per_gpu_bf16": dict(streams=128, precision="bf16", frames_per_call=64,
                                   desc="BASELINE configs[4] per-GPU partition: 128 streams/GPU (1024 over 8 GPUs), 10-minute clips fed in "
                                        "64-frame process() calls with the state carried across calls"),
@@ -356,6 +357,41 @@ class Runner:
             res["stream_major_call_fps"] = self.streams * e2e_steps / (time.perf_counter() - t0)
         return res
 
+    def host_link(self, mib=64, reps=12):
+        """What the host side of the end-to-end path can carry, measured in the same job with every rank copying at once: pinned
+        host <-> device copies of `mib` MiB in both directions simultaneously (the shape of the ingest path's traffic: one contiguous
+        chunk each way) and a plain host memcpy.  GB/s of THIS rank; the caller sums over ranks."""
+        torch = self.torch
+        n = mib << 20
+        h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+        d_in, d_out = torch.empty(n, dtype=torch.uint8, device=self.dev), torch.zeros(n, dtype=torch.uint8, device=self.dev)
+        s_in, s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        def both(k):
+            with torch.cuda.stream(s_in):
+                for _ in range(k):
+                    d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                for _ in range(k):
+                    h_out.copy_(d_out, non_blocking=True)
+        both(2)
+        torch.cuda.synchronize(self.dev)
+        self.barrier()
+        ev[0].record(s_in); ev[2].record(s_out)
+        both(reps)
+        ev[1].record(s_in); ev[3].record(s_out)
+        torch.cuda.synchronize(self.dev)
+        h2d = n * reps / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
+        d2h = n * reps / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9
+        a, b = np.empty(n * 2, np.uint8), np.ones(n * 2, np.uint8)
+        np.copyto(a, b)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            np.copyto(a, b)
+        host = 4 * a.nbytes / (time.perf_counter() - t0) / 1e9
+        return {"h2d_gbs": h2d, "d2h_gbs": d2h, "host_memcpy_gbs": host}
+
     def close(self):
         self.eng.delete()
 
@@ -375,7 +411,8 @@ def roofline_of(name, streams, precision, prof, prof_steps, timed_seconds, peaks
         peak, src = (1590.0, "fallback 1.59 PFLOP/s burst (B200_PROFILING.md), of fallback") if burst else (1400.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md), of fallback")
     achieved = dom_flops / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 if dom_n else None
     traffic, traffic_src = ncu_traffic(name) if streams == WORKLOADS[name]["streams"] else (None, "stream count overridden")
-    kernel = ("tc_fused_kernel (encoder + GRU layers + decoder GEMMs, all streams" + ("" if prof_steps == dom_n else f", {prof_steps // max(dom_n, 1)} steps per launch") + ")") if fused \
+    kernel = ("tc_fused_kernel (encoder + GRU layers + decoder GEMMs, all streams" + ("" if prof_steps == dom_n else f", {prof_steps // max(dom_n, 1)} steps per launch") +
+              (", fp32 operands as three bf16 planes: 3x the algorithmic flops are executed" if precision == "fp32" else "") + ")") if fused \
         else "gru_fp32_kernel (CUDA-core FMA GRU layer)"
     r = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": src,
@@ -431,6 +468,17 @@ def main():
                "note": "reference CPU engine not measurable (closed binary, needs AccessKey + licence server); "
                        "its CI ceilings: >456 frames/s cpu:1 on GitHub runners (BASELINE.md section 1)"}
 
+    # one rank = one GPU + its own slice of the host cores: the copy-issuing thread and the pinned buffers it first touches
+    # stay on cores no other rank uses (a no-op at N = 1)
+    cores = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            avail = sorted(os.sched_getaffinity(0))
+            per = max(1, len(avail) // world)
+            cores = avail[(local_rank * per) % len(avail):][:per]
+            os.sched_setaffinity(0, cores)
+        except OSError:
+            cores = None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -471,6 +519,7 @@ def main():
                      "ms_per_step": reduce(o_ms, MAX) / min(args.steps, 256), "gpu_launches_rank0": o_launches}
     e2e_steps = max(8, args.e2e_steps)
     e2e = run.e2e(e2e_steps)
+    link = run.host_link()
 
     ms = reduce(ms_local, MAX)
     total_frames = reduce(streams * args.steps, SUM)
@@ -479,6 +528,14 @@ def main():
     launches = int(reduce(launches_local, SUM))
     value = total_frames / (ms * 1e-3)
     e2e_value = e2e_frames / e2e_s
+    # the host's ceiling for the end-to-end metric: every frame crosses the link once each way (512 B in, 512 B out)
+    link_sum = {k: reduce(v, SUM) for k, v in link.items()}
+    link_min = {k: -reduce(-v, MAX) for k, v in link.items()}
+    ceiling = min(link_sum["h2d_gbs"], link_sum["d2h_gbs"]) * 1e9 / (FRAME * 2)
+    host_link = {"h2d_gbs": link_sum["h2d_gbs"], "d2h_gbs": link_sum["d2h_gbs"], "host_memcpy_gbs": link_sum["host_memcpy_gbs"],
+                 "per_rank_min": link_min, "ranks_copying_at_once": world, "cores_per_rank": len(cores) if cores else (os.cpu_count() or 1),
+                 "e2e_ceiling_frames_per_s": ceiling, "e2e_fraction_of_ceiling": e2e_value / ceiling,
+                 "how": "64 MiB pinned copies, both directions at once on two streams, all ranks at once (sum over ranks); ceiling = min(h2d, d2h) / 512 B per frame"}
     run.close()
 
     others = None
@@ -535,6 +592,7 @@ def main():
                     "api": "koala_b200.BatchKoala.process(pinned host tensor [steps][B][256], time_major=True) -> "
                            "pv_koala_batch_process_time_major, one call",
                     "one_step_per_call_value_rank0": e2e.get("one_step_per_call_fps"), "stream_major_call_value_rank0": e2e.get("stream_major_call_fps")},
+            "host_link": host_link,
             "gpu_launches": launches,
             "process_calls": calls_local,
             "one_frame_per_call": one_frame,

@@ -4,9 +4,11 @@
 //   tail [Bp][256] int16   previous input frame (analysis overlap)
 //   ola  [Bp][256] fp32    second half of the previous synthesis frame (bf16 path: [2][...] ping-pong by chunk, see backend_kernel)
 //   h    [L][Bp][H] fp32     recurrent state; bf16 path: updated in place, fp32 path: [2][...] ping-pong by step parity
-//   hb   [2][L][Bp][H] bf16  the same state rounded to bf16 = GEMM operand of the tensor-core path, ping-pong by step parity
-//                            (every unit tile reads all of h(t-1))
-// The bf16 path keeps all of the above in one arena (Engine::create).
+//   hb   [2][L][Bp][P H] bf16  the same state as GEMM operand of the tensor-core path, ping-pong by step parity (every unit tile
+//                            reads all of h(t-1)): P = 1 plane, h rounded to bf16, in bf16 mode; P = 3 planes hi | mid | lo that sum
+//                            to the fp32 value exactly in fp32 mode (masknet_fused.cuh)
+// The tensor-core path (both precisions, H a multiple of 256) keeps all of the above in one arena (Engine::create); fp32 mode
+// with another hidden size runs the CUDA-core kernels of masknet_fp32.cuh frame by frame.
 // Scratch: feat [T][Bp][256] (fp32 | bf16), spec [T][Bp][512] fp32, mask [T][Bp][256] fp32 for the T frames one chunk of the
 // bf16 path takes through its three launches (analysis of T frames -> fused mask estimator walking T steps -> synthesis of T
 // frames; T = chunk_frames() <= 64, sized so that the scratch stays under 512 MB), e [ring][Bp][H] (encoder output ring of
@@ -118,6 +120,7 @@ struct Engine::Impl {
     int parity = 0;   // h[parity] holds h(t-1)
     int tcap = 1;     // frames per chunk of the bf16 path (slots of feat / spec / mask)
     int e_ring = 1;   // slots of the encoder output ring
+    int planes = 1;   // bf16 planes per activation operand of the tensor-core path (3 in fp32 mode)
     int ola_par = 0;  // ola[ola_par] holds the overlap-add state
     int last_slot = 0;   // scratch slot of the last finished step (debug_read)
     // model
@@ -292,20 +295,25 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             }
         }
         KCHECK(upload(p->allocs, &p->tables, tab));
-        if (precision == kBf16) {
+        // fp32 mode runs on the tensor cores too when the model fits the fused kernel's tiles (three bf16 planes per operand);
+        // KOALA_FP32_CUDA_CORES=1 keeps the CUDA-core kernels (comparison runs)
+        const char *cc = getenv("KOALA_FP32_CUDA_CORES");
+        const bool fused = precision == kBf16 || (H % 256 == 0 && !(cc && cc[0] == '1'));
+        p->planes = precision == kFp32 ? 3 : 1;
+        if (fused) {
             // frames per chunk: as many as keep feat + spec + mask under 512 MB, at most 64 (KOALA_CHUNK_FRAMES overrides)
-            const size_t slot_bytes = Bp * (kNfft * 4 + kBins * 4 + kBins * 2);
+            const size_t slot_bytes = Bp * (kNfft * 4 + kBins * 4 + kBins * 2 * p->planes);
             int cap = 64;
             while (cap > 1 && (size_t) cap * slot_bytes > ((size_t) 512 << 20)) cap >>= 1;
             if (const char *e = getenv("KOALA_CHUNK_FRAMES")) cap = std::max(1, std::min(256, atoi(e)));
             p->tcap = cap;
-            p->e_ring = std::min(cap, kFuSlots);
-            if (const char *e = getenv("KOALA_E_RING")) p->e_ring = std::max(1, std::min(p->e_ring, atoi(e)));
+            p->e_ring = cap >= 4 ? 4 : cap >= 2 ? 2 : 1;      // a power of two <= kFuSlots
+            if (const char *e = getenv("KOALA_E_RING")) p->e_ring = atoi(e) >= 2 && p->e_ring >= 2 ? 2 : 1;
         }
-        const size_t T = p->tcap;
+        const size_t T = p->tcap, P = p->planes;
         KCHECK(dev_alloc(p->allocs, &p->spec, T * Bp * kNfft));
         KCHECK(dev_alloc(p->allocs, &p->mask, T * Bp * kBins));
-        if (precision == kFp32) {
+        if (!fused) {
             KCHECK(dev_alloc(p->allocs, &p->tail, Bp * kFrame));
             KCHECK(dev_alloc(p->allocs, &p->ola[0], Bp * kFrame));
             p->ola[1] = p->ola[0];
@@ -316,7 +324,7 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             // the overlap-add halves and the analysis tail.  In-place h takes 32 MB off the ~160 MB a step of 8192 streams touches
             // (126 MB L2): 90.4 -> 83.7 us per step.  (A persisting L2 access-policy window over the arena was tried and made
             // the step 44 % SLOWER -- the set-aside starves the per-step scratch -- so the arena uses the normal policy.)
-            const size_t h_bytes = L * Bp * H * sizeof(float), hb_bytes = L * Bp * H * sizeof(__nv_bfloat16);
+            const size_t h_bytes = L * Bp * H * sizeof(float), hb_bytes = L * Bp * P * H * sizeof(__nv_bfloat16);
             const size_t ola_bytes = Bp * kFrame * sizeof(float), tail_bytes = Bp * kFrame * sizeof(int16_t);
             p->arena_bytes = h_bytes + 2 * hb_bytes + 2 * ola_bytes + tail_bytes;
             KCHECK(dev_alloc(p->allocs, &p->arena, p->arena_bytes));
@@ -326,14 +334,14 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             for (int i = 0; i < 2; i++) { p->ola[i] = (float *) a; a += ola_bytes; }
             p->tail = (int16_t *) a;
         }
-        if (precision == kFp32) {
+        if (!fused) {
             KCHECK(dev_alloc(p->allocs, (float **) &p->feat, Bp * kBins));
             KCHECK(dev_alloc(p->allocs, (float **) &p->e, Bp * H));
         } else {
-            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->feat, T * Bp * kBins));
-            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->e, (size_t) p->e_ring * Bp * H));
+            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->feat, T * Bp * P * kBins));
+            KCHECK(dev_alloc(p->allocs, (__nv_bfloat16 **) &p->e, (size_t) p->e_ring * Bp * P * H));
             TcModel tm;
-            tm.H = (int) H; tm.L = (int) L; tm.Bp = (int) Bp; tm.tcap = p->tcap; tm.e_ring = p->e_ring;
+            tm.H = (int) H; tm.L = (int) L; tm.Bp = (int) Bp; tm.tcap = p->tcap; tm.e_ring = p->e_ring; tm.planes = p->planes;
             tm.enc_w = p->enc_w; tm.dec_w = p->dec_w; tm.enc_b = p->enc_b; tm.dec_b = p->dec_b;
             for (size_t l = 0; l < L; l++) { tm.wih[l] = p->wih[l]; tm.whh[l] = p->whh[l]; tm.bih[l] = p->bih[l]; tm.bhh[l] = p->bhh[l]; }
             tm.feat = (__nv_bfloat16 *) p->feat; tm.e = (__nv_bfloat16 *) p->e; tm.mask = p->mask;
@@ -412,14 +420,14 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     const size_t LBH = (size_t) Bp * H;
     KernelProfiler *prof = p->prof;
     static const bool only_masknet = [] { const char *e = getenv("KOALA_B200_ONLY_MASKNET"); return e && e[0] == '1'; }();
-    if (precision_ == kFp32) {
+    if (!p->fu) {          // fp32 mode, hidden size the fused kernel's tiles do not fit: CUDA-core kernels, frame by frame
         const int grid = stft_grid_for(B, p->num_sms, p->stft_per_warp);
         float *feat = (float *) p->feat, *e = (float *) p->e;
         for (int t = 0; t < frames; t++) {
             PcmView v{pcm, out, stride, out_stride, frame_stride, out_frame_stride, t};
             const int cur = p->parity, nxt = cur ^ 1;
             if (prof) prof->begin(kKernFrontend, st);
-            launch_pdl(false, frontend_kernel<float>, dim3(grid), dim3(kStftWarps * 32), 0, st, v, B, 1, (long long) Bp, p->tail, p->spec, feat, p->tables);
+            launch_pdl(false, frontend_kernel<float, 1>, dim3(grid), dim3(kStftWarps * 32), 0, st, v, B, 1, (long long) Bp, p->tail, p->spec, feat, p->tables);
             if (prof) { prof->end(st); prof->begin(kKernEnc, st); }
             launch_pdl(false, linear_fp32_kernel<kActRelu>, dim3(Bp / kF32Bm, H / kF32LinN), dim3(256), 0, st, feat, p->enc_w, p->enc_b, e, kBins, H);
             if (prof) prof->end(st);
@@ -443,7 +451,7 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
         KCHECK(cudaGetLastError());
         return kSuccess;
     }
-    // bf16 path: chunks of up to tcap frames, three launches per chunk chained with programmatic dependent launch
+    // tensor-core path: chunks of up to tcap frames, three launches per chunk chained with programmatic dependent launch
     const int resident_warps = p->num_sms * kStftCtasPerSm * kStftWarps;
     for (int t0 = 0; t0 < frames; t0 += p->tcap) {
         const int tc = std::min(p->tcap, frames - t0);
@@ -456,7 +464,8 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
             continue;
         }
         if (prof) prof->begin(kKernFrontend, st);
-        launch_pdl(true, frontend_kernel<__nv_bfloat16>, dim3(stft_grid_for(B * tc, p->num_sms, p->stft_per_warp)), dim3(kStftWarps * 32), 0, st, v, B, tc,
+        launch_pdl(true, p->planes == 1 ? frontend_kernel<__nv_bfloat16, 1> : frontend_kernel<__nv_bfloat16, 3>,
+                   dim3(stft_grid_for(B * tc, p->num_sms, p->stft_per_warp)), dim3(kStftWarps * 32), 0, st, v, B, tc,
                    (long long) Bp, p->tail, p->spec, (__nv_bfloat16 *) p->feat, p->tables);
         if (prof) { prof->end(st); prof->begin(kKernMasknet, st); }
         launches_ += 1 + fu_masknet_steps(p->fu, p->parity, tc, st);
@@ -575,7 +584,7 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
 }
 
 __global__ void reset_streams_kernel(const int32_t *__restrict__ ids, int n_ids, int n_streams, int16_t *tail, float *ola, float *ola1,
-                                     float *h0, float *h1, __nv_bfloat16 *hb0, __nv_bfloat16 *hb1, int H, int L, size_t LBH) {
+                                     float *h0, float *h1, __nv_bfloat16 *hb0, __nv_bfloat16 *hb1, int H, int L, size_t LBH, int planes) {
     const int i = blockIdx.x;
     if (i >= n_ids) return;
     const int s = ids[i];
@@ -590,11 +599,14 @@ __global__ void reset_streams_kernel(const int32_t *__restrict__ ids, int n_ids,
             const size_t idx = l * LBH + (size_t) s * H + k;
             h0[idx] = 0.0f;
             h1[idx] = 0.0f;
-            if (hb0) {
+        }
+    if (hb0)
+        for (int l = 0; l < L; l++)
+            for (int k = threadIdx.x; k < planes * H; k += blockDim.x) {
+                const size_t idx = (l * LBH + (size_t) s * H) * planes + k;
                 hb0[idx] = __float2bfloat16(0.0f);
                 hb1[idx] = __float2bfloat16(0.0f);
             }
-        }
 }
 
 Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> *errors) {
@@ -610,7 +622,7 @@ Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> 
         for (int i = 0; i < 2; i++) {
             KCHECK(cudaMemsetAsync(p->ola[i], 0, Bp * kFrame * sizeof(float), p->stream));
             KCHECK(cudaMemsetAsync(p->h[i], 0, L * Bp * H * sizeof(float), p->stream));
-            if (p->hb[i]) KCHECK(cudaMemsetAsync(p->hb[i], 0, L * Bp * H * sizeof(__nv_bfloat16), p->stream));
+            if (p->hb[i]) KCHECK(cudaMemsetAsync(p->hb[i], 0, L * Bp * p->planes * H * sizeof(__nv_bfloat16), p->stream));
         }
     } else {
         if (n < 0) {
@@ -627,7 +639,7 @@ Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> 
             KCHECK(cudaMalloc((void **) &d_ids, n * sizeof(int32_t)));
             cudaError_t e1 = cudaMemcpyAsync(d_ids, stream_ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream);
             reset_streams_kernel<<<n, 128, 0, p->stream>>>(d_ids, n, n_, p->tail, p->ola[0], p->ola[1], p->h[0], p->h[1], p->hb[0], p->hb[1],
-                                                          (int) H, (int) L, Bp * H);
+                                                          (int) H, (int) L, Bp * H, p->planes);
             cudaError_t e2 = cudaStreamSynchronize(p->stream);
             cudaFree(d_ids);
             KCHECK(e1);
@@ -681,7 +693,34 @@ Status Engine::debug_read(const char *name, void *dst, size_t bytes, std::vector
     const size_t esz = precision_ == kFp32 ? 4 : 2;
     const std::string nm(name ? name : "");
     // scratch of the last finished step: slot last_slot of the chunk buffers, ring slot (steps so far) % ring of e
-    const size_t slot = precision_ == kBf16 ? (size_t) p->last_slot : 0;
+    const size_t slot = p->fu ? (size_t) p->last_slot : 0;
+    if (p->fu && p->planes > 1 && (nm == "feat" || nm == "e")) {
+        // fp32 mode on the tensor-core path keeps these as three bf16 planes per row: hand out their sum, the fp32 value
+        const size_t cols = nm == "feat" ? (size_t) kBins : H, P = p->planes;
+        const size_t e_slot = p->fu->epoch > 0 ? (size_t) ((p->fu->epoch - 1) % p->e_ring) : 0;
+        const __nv_bfloat16 *base = nm == "feat" ? (const __nv_bfloat16 *) p->feat + slot * Bp * P * cols : (const __nv_bfloat16 *) p->e + e_slot * Bp * P * cols;
+        if (bytes > B * cols * 4) {
+            if (errors) errors->push_back("Unknown tensor name or size too large.");
+            return kInvalidArgument;
+        }
+        const size_t rows = (bytes / 4 + cols - 1) / cols;
+        std::vector<uint16_t> raw(rows * P * cols);
+        KCHECK(cudaMemcpy(raw.data(), base, raw.size() * 2, cudaMemcpyDeviceToHost));
+        std::vector<float> sum(rows * cols);
+        for (size_t r = 0; r < rows; r++)
+            for (size_t c = 0; c < cols; c++) {
+                float v = 0.0f;
+                for (size_t pl = P; pl-- > 0;) {          // small planes first: the sum is exact either way
+                    const uint32_t u = (uint32_t) raw[(r * P + pl) * cols + c] << 16;
+                    float f;
+                    memcpy(&f, &u, 4);
+                    v += f;
+                }
+                sum[r * cols + c] = v;
+            }
+        memcpy(dst, sum.data(), bytes);
+        return kSuccess;
+    }
     const size_t e_slot = (p->fu && p->fu->epoch > 0) ? (size_t) ((p->fu->epoch - 1) % p->e_ring) : 0;
     if (nm == "feat") { src = (const uint8_t *) p->feat + slot * Bp * kBins * esz; avail = B * kBins * esz; }
     else if (nm == "spec") { src = p->spec + slot * Bp * kNfft; avail = B * kNfft * 4; }

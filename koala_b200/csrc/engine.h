@@ -29,7 +29,8 @@ Status load_model_file(const char *path, ModelHost *out, std::vector<std::string
 
 class Engine {
 public:
-    // precision: 0 fp32 CUDA-core mask path, 1 bf16 tcgen05 mask path
+    // precision: 0 fp32 mask path (tcgen05 with three bf16 planes per activation when the hidden size is a multiple of 256, else
+    // CUDA-core kernels), 1 bf16 tcgen05 mask path
     static Status create(const ModelHost &model, int device, int num_streams, int precision, Engine **out,
                          std::vector<std::string> *errors);
     ~Engine();
@@ -41,7 +42,7 @@ public:
     // pcm / out: frame t of stream s at base + s * stride + t * frame_stride (int16 samples; frame_stride 256 for stream-major
     // buffers, streams * 256 with stride 256 for time-major ones).  Device pointers, 16-byte aligned, strides multiples of 8.
     // Enqueues `frames` consecutive steps on `stream` (a cudaStream_t taken literally: nullptr is the legacy default stream;
-    // own_stream() is the engine's private one) and returns without synchronising.  The bf16 path takes the frames in chunks of
+    // own_stream() is the engine's private one) and returns without synchronising.  The tensor-core path takes the frames in chunks of
     // up to chunk_frames(): analysis of the chunk, ONE fused mask-estimator launch walking its steps, synthesis of the chunk.
     Status process_device(const int16_t *pcm, int16_t *out, int frames, long long stride, void *stream,
                           std::vector<std::string> *errors, long long out_stride = 0 /* 0: same as stride */,

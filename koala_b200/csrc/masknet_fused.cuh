@@ -59,7 +59,6 @@ namespace koala {
 #ifndef KOALA_FU_STAGES
 #define KOALA_FU_STAGES 5
 #endif
-constexpr int kFuStages = KOALA_FU_STAGES;
 constexpr int kFuStageBytes = kTcABytes + (kGruRows / 2) * 128;   // 28 KB: A [128][64] + B up to [96][64] bf16 (linear tiles: 64 rows)
 constexpr int kFuCluster = 2;                                     // one CTA pair per cluster (4-CTA clusters with activation multicast: 2 % slower, r01)
 constexpr int kFuLinN = 128;                                      // outputs per linear pair tile
@@ -68,7 +67,16 @@ constexpr int kFuBoxB16 = kTcBlockM * 32 * 2;                     // staging box
 constexpr int kFuLinBytes = 2 * kFuBoxF32;                        // linear tiles: [128][128] bf16 (encoder) or one round of [128][64] fp32 (decoder)
 constexpr int kFuLinWarp = kTcStateWarp + 1;                      // stores the linear tiles' staged outputs
 constexpr int kFuThreads = 32 * (kFuLinWarp + 1);                 // 2 + 1 + 2 + 16 + 1 + 1 warps
-constexpr int kFuSmemBytes = kFuStages * kFuStageBytes + 2 * (kFuBoxF32 + kFuBoxB16) + kFuLinBytes + kTcTailBytes;
+// Operand PLANES.  bf16 mode: one plane, the activation rounded to bf16 (SPEC.md section 4, q = bf16_rne).  fp32 mode: three
+// planes hi | mid | lo with hi = bf16(v), mid = bf16(v - hi), lo = bf16(v - hi - mid): 3 x 8 significand bits = the whole fp32
+// value, and the weights ARE bf16 values, so W v = W hi + W mid + W lo with every product exact in the fp32 accumulator.  An
+// activation matrix is then [rows][planes * K] (plane p in columns p K ..), the k loop walks planes * K / 64 k-blocks and the
+// weight k-block index wraps: the same tile schedule, dependency counters and epilogues serve both modes.  The planes cost
+// 32 KB more staging, paid for with operand stages (3 instead of 5): fp32 mode is for small batches, which are latency-bound.
+template <int kPlanes> struct FuCfg {
+    static constexpr int kStages = kPlanes == 1 ? KOALA_FU_STAGES : 3;
+    static constexpr int kSmemBytes = kStages * kFuStageBytes + 2 * (kFuBoxF32 + kPlanes * kFuBoxB16) + kFuLinBytes + kTcTailBytes;
+};
 constexpr int kFuMaxSegs = kMaxLayers + 2;
 constexpr int kFuArrivals = kTcEpiWarps;                          // epilogue barriers: one arrival per warp (after __syncwarp), not per thread
 constexpr int kFuSlots = 4;                                       // step slots per dependency counter row (>= encoder ring, >= 3)
@@ -77,18 +85,19 @@ enum FuMap : int { kMapA0 = 0, kMapA1, kMapB0, kMapB1, kMapHp, kMapHn, kMapHb, k
 struct FuSeg {
     int mode;                 // kTcEnc | kTcGru | kTcDec
     int n_tiles;              // pair tiles along n
-    int kb_per_part, parts;   // k-blocks of 64 per operand part; GRU has two parts (x and h)
+    unsigned n_magic;         // ceil(2^32 / n_tiles): index / n_tiles = umulhi(index, n_magic) for index < 65536
+    int kb_per_part, parts;   // k-blocks of 64 per operand part (all planes); GRU has two parts (x and h)
+    int kb_w;                 // k-blocks of one weight row = kb_per_part / planes
     int step_delta;           // a tile of this segment in period p belongs to step p - 1 + step_delta (encoder +1, decoder -1)
     int x_first;              // GRU: the x part runs before the h part
     unsigned inc;             // what one step adds to this segment's counter of an m tile (2 CTAs per n tile)
     const float *bias0, *bias1;
-    int a0_rows, a1_rows, b_rows;   // KOALA_FU_FAKE_KB timing experiment: rows of the operand matrices
 };
 struct FuArgs {
     int nseg, num_m_tiles, tiles_per_step, total_tiles, H, Bp;
     int steps;                // frames in this launch
     int cur0;                 // parity of the state buffers that hold h(t-1) of the launch's first step
-    int e_ring;               // slots of the encoder-output ring (slot = global step % e_ring), <= kFuSlots
+    int e_ring;               // slots of the encoder-output ring (slot = global step % e_ring): a power of two <= kFuSlots
     long long epoch0;         // steps completed before this launch = global index of the launch's first step
     unsigned *counters;       // [nseg][num_m_tiles][kFuSlots]
     const CUtensorMap *maps;  // [2 parities][nseg][kFuMapsPerSeg], global memory
@@ -131,38 +140,58 @@ struct FuTile {
     int par;                  // parity of the state buffers that hold h(t-1) of this step
     long long g;              // global step index (0-based): epoch0 + t
 };
-__device__ __forceinline__ FuTile fu_decode(const FuArgs &a, int g) {
+// A role's walk over its pair's list positions g = cluster, cluster + stride, ...  Every role of every CTA decodes every tile it
+// touches, the MMA issuer between two k loops: with a division per field the decode was ~600 cycles of a ~9 k-cycle GRU tile
+// on the tensor pipe's critical path (r02i trace), so the period / offset pair is carried along instead of being recomputed,
+// and the one remaining quotient is a multiplication.
+struct FuIter {
+    int g, p, local;          // list position, its period, its index inside the period
+};
+__device__ __forceinline__ void fu_iter_init(const FuArgs &a, FuIter &it, int g) {
+    it.g = g;
+    it.p = g / a.tiles_per_step;
+    it.local = g - it.p * a.tiles_per_step;
+}
+__device__ __forceinline__ void fu_iter_advance(const FuArgs &a, FuIter &it, int stride) {
+    it.g += stride;
+    it.local += stride;
+    while (it.local >= a.tiles_per_step) {
+        it.local -= a.tiles_per_step;
+        ++it.p;
+    }
+}
+__device__ __forceinline__ FuTile fu_tile_at(const FuArgs &a, const FuIter &it) {
     FuTile r;
-    const int p = g / a.tiles_per_step, local = g - p * a.tiles_per_step;
     int i = 0;
-    while (i + 1 < a.nseg && local >= a.pos_begin[i + 1]) ++i;
-    const int s = a.pos_seg[i], in_seg = local - a.pos_begin[i], nt = a.seg[s].n_tiles;
-    r.t = p - 1 + a.seg[s].step_delta;
+    while (i + 1 < a.nseg && it.local >= a.pos_begin[i + 1]) ++i;
+    const int s = a.pos_seg[i], in_seg = it.local - a.pos_begin[i];
+    r.t = it.p - 1 + a.seg[s].step_delta;
     r.s = (r.t >= 0 && r.t < a.steps) ? s : -1;
-    r.m = in_seg / nt;
-    r.n = in_seg - r.m * nt;
+    r.m = (int) __umulhi((unsigned) in_seg, a.seg[s].n_magic);
+    r.n = in_seg - r.m * a.seg[s].n_tiles;
     r.par = (a.cur0 + r.t) & 1;
     r.g = a.epoch0 + r.t;
     return r;
 }
-// the pair's next tile at or after list position g (stride = pairs in the grid); false when the list is exhausted
-__device__ __forceinline__ bool fu_next(const FuArgs &a, int &g, int stride, FuTile &t) {
-    for (; g < a.total_tiles; g += stride) {
-        t = fu_decode(a, g);
+// the pair's next tile at or after the iterator's position; false when the list is exhausted
+__device__ __forceinline__ bool fu_next(const FuArgs &a, FuIter &it, int stride, FuTile &t) {
+    for (; it.g < a.total_tiles; fu_iter_advance(a, it, stride)) {
+        t = fu_tile_at(a, it);
         if (t.s >= 0) return true;
     }
     return false;
 }
+__device__ __forceinline__ int fu_slot(long long g) { return (int) ((unsigned long long) g & (kFuSlots - 1)); }
 // "segment s has finished global step g for m tile m": the counter and the value it has reached by then.  False: nothing to
 // wait for (before the engine's first step).
 __device__ __forceinline__ bool fu_done_ctr(const FuArgs &a, int s, int m, long long g, const unsigned *&ctr, unsigned &target) {
     if (g < 0) return false;
-    ctr = a.counters + ((size_t) s * a.num_m_tiles + m) * kFuSlots + (int) (g % kFuSlots);
-    target = (unsigned) (g / kFuSlots + 1) * a.seg[s].inc;
+    ctr = a.counters + ((size_t) s * a.num_m_tiles + m) * kFuSlots + fu_slot(g);
+    target = ((unsigned) ((unsigned long long) g / kFuSlots) + 1u) * a.seg[s].inc;
     return true;
 }
 __device__ __forceinline__ void fu_signal_done(const FuArgs &a, const FuTile &t) {
-    red_release_gpu(a.counters + ((size_t) t.s * a.num_m_tiles + t.m) * kFuSlots + (int) (t.g % kFuSlots), 1u);
+    red_release_gpu(a.counters + ((size_t) t.s * a.num_m_tiles + t.m) * kFuSlots + fu_slot(t.g), 1u);
 }
 // the two dependencies of a tile's loads: (x) previous segment, same step; (h) own segment, previous step
 __device__ __forceinline__ bool fu_dep_x(const FuArgs &a, const FuTile &t, const unsigned *&ctr, unsigned &target) {
@@ -192,14 +221,15 @@ struct FuDep {
     __device__ __forceinline__ void wait() { if (!holds()) { fu_wait_counter(ctr, target); seen = target; } }
 };
 
+template <int kPlanes>
 __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads, 1) tc_fused_kernel(const __grid_constant__ FuArgs args) {
-    constexpr int kStages = kFuStages, kStageBytes = kFuStageBytes;
+    constexpr int kStages = FuCfg<kPlanes>::kStages, kStageBytes = kFuStageBytes;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
     uint8_t *s_f32 = smem + kStages * kStageBytes;       // 2 fp32 staging boxes
-    uint8_t *s_b16 = s_f32 + 2 * kFuBoxF32;              // 2 bf16 staging boxes
-    uint8_t *s_lin = s_b16 + 2 * kFuBoxB16;              // linear tiles' staging: two 16 KB swizzled boxes
+    uint8_t *s_b16 = s_f32 + 2 * kFuBoxF32;              // 2 x kPlanes bf16 staging boxes
+    uint8_t *s_lin = s_b16 + 2 * kPlanes * kFuBoxB16;    // linear tiles' staging: two 16 KB swizzled boxes
     uint8_t *tail = s_lin + kFuLinBytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
     uint64_t *full_bar = bars, *empty_bar = bars + kStages;
@@ -228,6 +258,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
     pdl_launch_dependents();
     const int cluster_id = blockIdx.x / kFuCluster, num_clusters = gridDim.x / kFuCluster;
     const int total = args.total_tiles;   // list positions (valid or not)
+    const int ring_mask = args.e_ring - 1;
 
     if (warp == 0) {
         for (int i = lane; i < 2 * args.nseg * kFuMapsPerSeg; i += 32) prefetch_tmap(args.maps + i);
@@ -271,19 +302,21 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         unsigned seen_x = 0, seen_h = 0;    // the next tile's dependency counters, sampled one tile early (hides the L2 round trip)
         bool have_seen = false;
         FuTile t, t1;
-        int g = cluster_id, g1 = 0;
-        bool have = fu_next(args, g, num_clusters, t), have1 = false;
-        for (; have; g = g1, t = t1, have = have1, ++pit) {
+        FuIter it, it1;
+        fu_iter_init(args, it, cluster_id);
+        it1 = it;
+        bool have = fu_next(args, it, num_clusters, t), have1 = false;
+        for (; have; it = it1, t = t1, have = have1, ++pit) {
             const FuSeg &sg = args.seg[t.s];
             const CUtensorMap *maps = args.maps + (size_t) (t.par * args.nseg + t.s) * kFuMapsPerSeg;
             const bool gru = sg.mode == kTcGru;
-            const int kbp = sg.kb_per_part, num_kb = kbp * sg.parts;
+            const int kbp = sg.kb_per_part, num_kb = kbp * sg.parts, kbw = sg.kb_w;
             const int brows = gru ? kGruRows / 2 : kFuLinN / 2;         // weight rows each CTA of the pair holds
             const uint32_t pair_tx = 2u * (uint32_t) (kTcABytes + brows * 128);
             const int hpart = gru ? (sg.x_first ? 1 : 0) : -1;          // position of the h part in the k loop
             // x operand rows: features of slot t (encoder), encoder-output ring slot (GRU layer 0), else a state copy
             const int a0_row = t.m * kTcPairM + arow +
-                               (sg.mode == kTcEnc ? t.t * args.Bp : t.s == 1 ? (int) (t.g % args.e_ring) * args.Bp : 0);
+                               (sg.mode == kTcEnc ? t.t * args.Bp : t.s == 1 ? ((int) t.g & ring_mask) * args.Bp : 0);
             const int a1_row = t.m * kTcPairM + arow;
             const unsigned my_seen_x = seen_x, my_seen_h = seen_h;
             const bool my_have = have_seen;
@@ -305,24 +338,22 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 if (elected && is_a && rank == 0) mbar_expect_tx(&full_bar[stage], pair_tx);
                 const uint32_t full_leader = map_to_cta(&full_bar[stage], leader);
                 uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kTcABytes;
-                const int kc = (kb - part * kbp) * kTcBlockK;
+                int kbi = kb - part * kbp;                  // k-block inside the operand part: activation column block ...
+                if (!is_a && kPlanes > 1) {                 // ... the weights repeat for every plane
+                    while (kbi >= kbw) kbi -= kbw;
+                }
+                const int kc = kbi * kTcBlockK;
                 if (!elected) {
-#ifdef KOALA_FU_FAKE_KB    // timing experiment: the same bytes as contiguous [rows][64] boxes of a K-blocked view of the same memory (wrong data)
-                } else if (is_a) {
-                    tma_load_2d_pair(maps + (hp ? kMapA1 : kMapA0), full_leader, sa, 0, (kc / kTcBlockK) * (hp ? sg.a1_rows : sg.a0_rows) + (hp ? a1_row : a0_row));
-                } else {
-                    tma_load_2d_pair(maps + (hp ? kMapB1 : kMapB0), full_leader, sb, 0, (kc / kTcBlockK) * sg.b_rows + t.n * 2 * brows + (int) rank * brows);
-#else
                 } else if (is_a) {
                     tma_load_2d_pair(maps + (hp ? kMapA1 : kMapA0), full_leader, sa, kc, hp ? a1_row : a0_row);
                 } else {
                     tma_load_2d_pair(maps + (hp ? kMapB1 : kMapB0), full_leader, sb, kc, t.n * 2 * brows + (int) rank * brows);
-#endif
                 }
                 __syncwarp();
                 if (kb == par) {         // my first load of the tile is on its way: decode the pair's next tile behind it
-                    g1 = g + num_clusters;
-                    have1 = fu_next(args, g1, num_clusters, t1);
+                    it1 = it;
+                    fu_iter_advance(args, it1, num_clusters);
+                    have1 = fu_next(args, it1, num_clusters, t1);
                     if (have1) {
                         if (is_a) {
                             const unsigned *ctr = nullptr;
@@ -346,8 +377,9 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             unsigned kb_total = 0;           // k-blocks issued so far: every lane derives the pipeline position from it
             const uint64_t adesc0 = make_sw128_desc(smem_u32(smem)), bdesc0 = make_sw128_desc(smem_u32(smem) + kTcABytes);
             FuTile t, t_next;
-            int g = cluster_id;
-            bool have = fu_next(args, g, num_clusters, t);
+            FuIter pos;
+            fu_iter_init(args, pos, cluster_id);
+            bool have = fu_next(args, pos, num_clusters, t);
             for (; have; ++it) {
                 const FuSeg &sg = args.seg[t.s];
                 const bool gru = sg.mode == kTcGru;
@@ -357,8 +389,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 const int ab = it & 1, aphase = (it >> 1) & 1;
                 // the next tile is decoded here, in front of this tile's barrier waits, which absorb it: decoded after the k
                 // loop it was ~600 idle cycles of the tensor pipe per tile (r02d trace)
-                g += num_clusters;
-                have = fu_next(args, g, num_clusters, t_next);
+                fu_iter_advance(args, pos, num_clusters);
+                have = fu_next(args, pos, num_clusters, t_next);
                 mbar_wait(&tmem_empty[ab], aphase);      // both CTAs' epilogues have released (and cleared) this buffer
                 tc_fence_after();
                 if (lane == 0) KTRACE(it, 2);
@@ -406,18 +438,19 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         if (elect_one()) {
             const int row0 = (int) rank * kTcBlockM;
             struct PassIter {
+                FuIter it;
                 int g, c;
                 FuTile t;
                 FuDep h, w;      // the tile's (h) and (w) dependencies, sampled when the iterator reaches the tile
             };
-            auto start = [&](PassIter &p, int g) {           // first pass of the pair's next GRU tile at or after g
-                for (; fu_next(args, g, num_clusters, p.t); g += num_clusters)
+            auto start = [&](PassIter &p) {                  // first pass of the pair's next GRU tile at or after p.it
+                for (; fu_next(args, p.it, num_clusters, p.t); fu_iter_advance(args, p.it, num_clusters))
                     if (args.seg[p.t.s].mode == kTcGru) break;
-                p.g = g;
+                p.g = p.it.g;
                 p.c = 0;
                 p.h.none();
                 p.w.none();
-                if (g < total) {
+                if (p.g < total) {
                     fu_dep_h(args, p.t, p.h.ctr, p.h.target);
                     fu_dep_w(args, p.t, p.w.ctr, p.w.target);
                     p.h.sample();
@@ -425,10 +458,14 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 }
             };
             auto advance = [&](PassIter &p) {
-                if (++p.c == 2) start(p, p.g + num_clusters);
+                if (++p.c == 2) {
+                    fu_iter_advance(args, p.it, num_clusters);
+                    start(p);
+                }
             };
             PassIter cur, ahead;
-            start(cur, cluster_id);
+            fu_iter_init(args, cur.it, cluster_id);
+            start(cur);
             ahead = cur;
             unsigned armed = 0, pc = 0;      // passes requested / stored so far; pass q uses staging buffer q & 1
             auto try_arm = [&](bool block) {
@@ -454,7 +491,9 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 mbar_wait(&staged[buf], (pc >> 1) & 1);
                 if (cur.c == 0) cur.w.wait();
                 tma_store_2d(maps + kMapHn, s_f32 + buf * kFuBoxF32, col, row);
-                tma_store_2d(maps + kMapHb, s_b16 + buf * kFuBoxB16, col, row);
+#pragma unroll
+                for (int pl = 0; pl < kPlanes; ++pl)         // bf16 copy (fp32 mode: its three planes) = the operand of the next tiles
+                    tma_store_2d(maps + kMapHb, s_b16 + (buf * kPlanes + pl) * kFuBoxB16, col + pl * args.H, row);
                 bulk_commit();
                 KTRACE((cur.g - cluster_id) / num_clusters, 9 + (cur.c & 1) * 2);
                 bulk_wait_read();                            // the stores have read buffer `buf`
@@ -481,7 +520,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             const int row0 = (int) rank * kTcBlockM;
             unsigned n16 = 0, n8 = 0;
             FuTile t;
-            for (int g = cluster_id; fu_next(args, g, num_clusters, t); g += num_clusters) {
+            FuIter pos;
+            for (fu_iter_init(args, pos, cluster_id); fu_next(args, pos, num_clusters, t); fu_iter_advance(args, pos, num_clusters)) {
                 const FuSeg &sg = args.seg[t.s];
                 if (sg.mode == kTcGru) continue;
                 const CUtensorMap *map = args.maps + (size_t) (t.par * args.nseg + t.s) * kFuMapsPerSeg + kMapHn;
@@ -490,15 +530,17 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 w.none();
                 fu_dep_w(args, t, w.ctr, w.target);
                 w.sample();                        // looked at after the wait for the staged tile
-                if (sg.mode == kTcEnc) {           // two boxes of 64 bf16 columns into ring slot G % ring
-                    const int row = t.m * kTcPairM + row0 + (int) (t.g % args.e_ring) * args.Bp;
-                    mbar_wait(lin_staged16, n16++ & 1);
-                    w.wait();
-                    tma_store_2d(map, s_lin, col, row);
-                    tma_store_2d(map, s_lin + kFuBoxF32, col + 64, row);
-                    bulk_commit();
-                    bulk_wait_read();
-                    mbar_arrive(lin_free);
+                if (sg.mode == kTcEnc) {           // per plane: two boxes of 64 bf16 columns into ring slot G % ring
+                    const int row = t.m * kTcPairM + row0 + ((int) t.g & ring_mask) * args.Bp;
+                    for (int pl = 0; pl < kPlanes; ++pl) {
+                        mbar_wait(lin_staged16, n16++ & 1);
+                        if (pl == 0) w.wait();
+                        tma_store_2d(map, s_lin, col + pl * args.H, row);
+                        tma_store_2d(map, s_lin + kFuBoxF32, col + pl * args.H + 64, row);
+                        bulk_commit();
+                        bulk_wait_read();
+                        mbar_arrive(lin_free);
+                    }
                 } else {                           // two rounds of two boxes of 32 fp32 columns into mask slot t
                     const int row = t.m * kTcPairM + row0 + t.t * args.Bp;
                     for (int r = 0; r < 2; ++r) {
@@ -546,7 +588,8 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         unsigned pc = 0, lf = 0;       // GRU passes / linear rounds so far: staging buffer and barrier phase
         int it = 0;
         FuTile t;
-        for (int g = cluster_id; fu_next(args, g, num_clusters, t); g += num_clusters, ++it) {
+        FuIter pos;
+        for (fu_iter_init(args, pos, cluster_id); fu_next(args, pos, num_clusters, t); fu_iter_advance(args, pos, num_clusters), ++it) {
             const FuSeg &sg = args.seg[t.s];
             const int mode = sg.mode, n = t.n;
             const int ab = it & 1, aphase = (it >> 1) & 1;
@@ -592,15 +635,21 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                     acc[i] = mode == kTcEnc ? fmaxf(v, 0.0f) : sigmoid_f(v);
                 }
                 if (mode == kTcEnc) {                        // box part / 2 holds columns 64 (part / 2) ..; my 32 columns = 4 chunks of 8 bf16
-                    mbar_wait(lin_free, (lf & 1) ^ 1);       // the previous linear round's stores have read the staging boxes
                     uint8_t *rowp = s_lin + (part >> 1) * kFuBoxF32 + row_in_cta * 128;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + j) ^ sw) << 4)) = pack_bf16x8(acc + 8 * j);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(lin_staged16);
-                    lf += 1;
+                    for (int pl = 0; pl < kPlanes; ++pl) {   // one round per plane: what is staged is subtracted, the rest goes to the next plane
+                        mbar_wait(lin_free, ((lf + (unsigned) pl) & 1) ^ 1);   // the previous linear round's stores have read the staging boxes
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 u = pack_bf16x8(acc + 8 * j);
+                            *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + j) ^ sw) << 4)) = u;
+                            if (pl + 1 < kPlanes) sub_bf16x8(acc + 8 * j, u);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(lin_staged16);
+                    }
+                    lf += kPlanes;
                 } else {                                     // round part / 2, box part & 1: my 32 fp32 columns = 8 chunks of 4
                     mbar_wait(lin_free, ((lf + (unsigned) (part >> 1)) & 1) ^ 1);
                     uint8_t *rowp = s_lin + (part & 1) * kFuBoxF32 + row_in_cta * 128;
@@ -618,7 +667,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
             for (int c = 0; c < 2; ++c, ++pc) {
                 const int buf = (int) (pc & 1);
                 uint8_t *f32_row = s_f32 + buf * kFuBoxF32 + row_in_cta * 128;
-                uint8_t *b16_row = s_b16 + buf * kFuBoxB16 + row_in_cta * 64;
+                uint8_t *b16_row = s_b16 + buf * kPlanes * kFuBoxB16 + row_in_cta * 64;
                 const int cu = c * 32 + part * 8;            // first of my 8 units inside the tile
                 float anx[8], ar[8], az[8], anh[8], hp[8], out[8];
                 tmem_ld8(t0 + 0 + cu, anx);
@@ -660,7 +709,12 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
                 for (int q = 0; q < 2; ++q)                  // h(t) replaces h(t-1) in place
                     *reinterpret_cast<float4 *>(f32_row + (((part * 2 + q) ^ sw) << 4)) =
                         make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
-                *reinterpret_cast<uint4 *>(b16_row + part * 16) = pack_bf16x8(out);
+#pragma unroll
+                for (int pl = 0; pl < kPlanes; ++pl) {
+                    const uint4 u = pack_bf16x8(out);
+                    *reinterpret_cast<uint4 *>(b16_row + pl * kFuBoxB16 + part * 16) = u;
+                    if (pl + 1 < kPlanes) sub_bf16x8(out, u);
+                }
                 fence_proxy_async();                         // my smem writes -> visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&staged[buf]);    // the state warp stores the pass once everybody is here
@@ -682,7 +736,7 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
 // ---------------------------------------------------------------------------------------------------------------
 // host side: tensor maps and segment tables for both state parities, the dependency counters, the launch
 struct FuPlan {
-    int nseg = 0, max_clusters = 0, num_sms = 0, tcap = 1;
+    int nseg = 0, max_clusters = 0, num_sms = 0, tcap = 1, planes = 1;
     __nv_bfloat16 *wih_p[kMaxLayers] = {}, *whh_p[kMaxLayers] = {};   // GRU weights packed per 64-unit tile (pack_gru_weights_kernel)
     long long epoch = 0;              // steps completed by accepted launches
     unsigned *counters = nullptr;
@@ -703,10 +757,17 @@ static void fu_plan_destroy(FuPlan *f) {
     delete f;
 }
 
-// `m.feat` / `m.mask` hold m.tcap step slots of [Bp] rows, `m.e` holds m.e_ring slots
+typedef void (*FuKernel)(const FuArgs);
+static FuKernel fu_kernel(int planes) { return planes == 1 ? tc_fused_kernel<1> : tc_fused_kernel<3>; }
+static int fu_smem_bytes(int planes) { return planes == 1 ? FuCfg<1>::kSmemBytes : FuCfg<3>::kSmemBytes; }
+
+// `m.feat` / `m.mask` hold m.tcap step slots of [Bp] rows, `m.e` holds m.e_ring slots; activation matrices (feat, e, hb) have
+// m.planes * K columns
 static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
-    if (m.H % 256 != 0 || m.Bp % kTcPairM != 0) {
-        *why = "hidden size must be a multiple of 256 and the padded stream count a multiple of 256 for the tensor-core path";
+    if (m.H % 256 != 0 || m.Bp % kTcPairM != 0 || (m.planes != 1 && m.planes != 3) || (m.e_ring & (m.e_ring - 1)) != 0 ||
+        (size_t) (m.Bp / kTcPairM) * (m.H / kGruUnits) >= 65536) {
+        *why = "hidden size must be a multiple of 256, the padded stream count a multiple of 256 (at most 2 M streams at H = 512) and the "
+               "encoder ring a power of two for the tensor-core path";
         return false;
     }
     void *fnp = nullptr;
@@ -722,6 +783,10 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
     const int mt = m.Bp / kTcPairM, nseg = m.L + 2;
     f->nseg = nseg;
     f->tcap = m.tcap;
+    f->planes = m.planes;
+    const uint64_t P = (uint64_t) m.planes;
+    FuKernel kernel = fu_kernel(m.planes);
+    const int smem_bytes = fu_smem_bytes(m.planes);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&f->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -740,19 +805,19 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
         if (tr[0] == '1' && cudaMalloc((void **) &f->trace, 2048 * sizeof(long long)) == cudaSuccess) cudaMemset(f->trace, 0, 2048 * sizeof(long long));
         if (const char *sk = getenv("KOALA_FU_TRACE_SKIP")) trace_skip = atoi(sk);
     }
-    ok = ok && cudaFuncSetAttribute(tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) == cudaSuccess;
     int resident_pairs = f->num_sms / kFuCluster;      // CTA pairs the device can hold at once
     if (ok) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned) (kFuCluster * f->num_sms));
         cfg.blockDim = dim3(kFuThreads);
-        cfg.dynamicSmemBytes = (size_t) kFuSmemBytes;
+        cfg.dynamicSmemBytes = (size_t) smem_bytes;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = kFuCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, tc_fused_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = f->num_sms / kFuCluster - 4; }
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = f->num_sms / kFuCluster - 4; }
         resident_pairs = n;
         if (const char *e = getenv("KOALA_FU_CLUSTERS")) n = std::max(1, std::min(n, atoi(e)));
         f->max_clusters = n;
@@ -764,16 +829,18 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
     for (int s = 0; s < nseg; s++) {
         FuSeg &sg = a.seg[s];
         if (s == 0) {                                  // encoder: e = relu(feat W_enc^T + b)
-            sg.mode = kTcEnc; sg.n_tiles = m.H / kFuLinN; sg.kb_per_part = kBins / kTcBlockK; sg.parts = 1; sg.step_delta = 1;
+            sg.mode = kTcEnc; sg.n_tiles = m.H / kFuLinN; sg.kb_w = kBins / kTcBlockK; sg.parts = 1; sg.step_delta = 1;
             sg.bias0 = m.enc_b;
         } else if (s == nseg - 1) {                    // decoder: mask = sigmoid(h_{L-1}(t) W_dec^T + b)
-            sg.mode = kTcDec; sg.n_tiles = kBins / kFuLinN; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 1; sg.step_delta = -1;
+            sg.mode = kTcDec; sg.n_tiles = kBins / kFuLinN; sg.kb_w = m.H / kTcBlockK; sg.parts = 1; sg.step_delta = -1;
             sg.bias0 = m.dec_b;
         } else {                                       // GRU layer l
             const size_t l = s - 1;
-            sg.mode = kTcGru; sg.n_tiles = m.H / kGruUnits; sg.kb_per_part = m.H / kTcBlockK; sg.parts = 2; sg.step_delta = 0;
+            sg.mode = kTcGru; sg.n_tiles = m.H / kGruUnits; sg.kb_w = m.H / kTcBlockK; sg.parts = 2; sg.step_delta = 0;
             sg.bias0 = m.bih[l]; sg.bias1 = m.bhh[l];
         }
+        sg.kb_per_part = sg.kb_w * m.planes;
+        sg.n_magic = (unsigned) ((((uint64_t) 1 << 32) + sg.n_tiles - 1) / sg.n_tiles);
         sg.inc = (unsigned) (2 * sg.n_tiles);          // the rows of an m tile are written by both CTAs of every n tile
     }
     // list order inside a period: GRU layer 0, decoder (a step behind), encoder (a step ahead), GRU layers 1..
@@ -801,33 +868,26 @@ static bool fu_plan_create(const TcModel &m, FuPlan **out, std::string *why) {
             bool used[kFuMapsPerSeg] = {};
             auto put = [&](int k, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool f32 = false, bool plain32 = false) {
                 used[k] = true;
-#ifdef KOALA_FU_FAKE_KB
-                if (k == kMapA0 || k == kMapA1 || k == kMapB0 || k == kMapB1) {
-                    (k == kMapA0 ? a.seg[s].a0_rows : k == kMapA1 ? a.seg[s].a1_rows : a.seg[s].b_rows) = (int) rows;
-                    rows *= cols / kTcBlockK;
-                    cols = kTcBlockK;
-                }
-#endif
                 ok = ok && encode_2d(fn, &mp[k], base, rows, cols, box_rows, f32, plain32);
             };
             if (s == 0) {
-                put(kMapA0, m.feat, (uint64_t) m.tcap * Bp, kBins, kTcBlockM);
+                put(kMapA0, m.feat, (uint64_t) m.tcap * Bp, P * kBins, kTcBlockM);
                 put(kMapB0, m.enc_w, H, kBins, kFuLinN / 2);
-                put(kMapHn, m.e, (uint64_t) m.e_ring * Bp, H, kTcBlockM);     // store map: boxes of 64 bf16 columns x 128 rows, 128B swizzle
+                put(kMapHn, m.e, (uint64_t) m.e_ring * Bp, P * H, kTcBlockM);     // store map: boxes of 64 bf16 columns x 128 rows, 128B swizzle
             } else if (s == nseg - 1) {
-                put(kMapA0, m.hb[nxt] + (L - 1) * LBH, Bp, H, kTcBlockM);
+                put(kMapA0, m.hb[nxt] + (L - 1) * P * LBH, Bp, P * H, kTcBlockM);
                 put(kMapB0, m.dec_w, kBins, H, kFuLinN / 2);
                 put(kMapHn, m.mask, (uint64_t) m.tcap * Bp, kBins, kTcBlockM, true);    // store map: boxes of 32 fp32 columns x 128 rows, 128B swizzle
             } else {
                 const size_t l = s - 1;
-                if (l == 0) put(kMapA0, m.e, (uint64_t) m.e_ring * Bp, H, kTcBlockM);
-                else put(kMapA0, m.hb[nxt] + (l - 1) * LBH, Bp, H, kTcBlockM);
-                put(kMapA1, m.hb[cur] + l * LBH, Bp, H, kTcBlockM);
+                if (l == 0) put(kMapA0, m.e, (uint64_t) m.e_ring * Bp, P * H, kTcBlockM);
+                else put(kMapA0, m.hb[nxt] + (l - 1) * P * LBH, Bp, P * H, kTcBlockM);
+                put(kMapA1, m.hb[cur] + l * P * LBH, Bp, P * H, kTcBlockM);
                 put(kMapB0, f->wih_p[l], 3 * H, H, kGruRows / 2);
                 put(kMapB1, f->whh_p[l], 3 * H, H, kGruRows / 2);
                 put(kMapHp, m.h[cur] + l * LBH, Bp, H, kTcBlockM, true);
                 put(kMapHn, m.h[nxt] + l * LBH, Bp, H, kTcBlockM, true);
-                put(kMapHb, m.hb[nxt] + l * LBH, Bp, H, kTcBlockM, false, true);
+                put(kMapHb, m.hb[nxt] + l * P * LBH, Bp, P * H, kTcBlockM, false, true);
             }
             for (int k = 0; k < kFuMapsPerSeg; k++)        // unused slots: any valid descriptor (they are only prefetched)
                 if (!used[k]) mp[k] = mp[kMapA0];
@@ -857,7 +917,7 @@ static int fu_masknet_steps(FuPlan *f, int cur, int steps, cudaStream_t st) {
     const int clusters = steps * a.tiles_per_step < f->max_clusters ? steps * a.tiles_per_step : f->max_clusters;
     // the epoch only advances with a launch that was accepted: the counters then stand at epoch * (increments per step), which
     // is what the next launch waits for (the caller reports the launch error through cudaGetLastError)
-    if (launch_pdl(true, tc_fused_kernel, dim3((unsigned) (kFuCluster * clusters)), dim3(kFuThreads), (size_t) kFuSmemBytes, st, a) == cudaSuccess)
+    if (launch_pdl(true, fu_kernel(f->planes), dim3((unsigned) (kFuCluster * clusters)), dim3(kFuThreads), (size_t) fu_smem_bytes(f->planes), st, a) == cudaSuccess)
         f->epoch += steps;
     return 1;
 }

@@ -20,9 +20,18 @@ namespace koala {
 constexpr int kStftWarps = 4;         // warps (= streams in flight) per CTA
 constexpr int kStftCtasPerSm = KOALA_STFT_CTAS;     // resident CTAs per SM the register budget is sized for
 
-template <typename FeatT> __device__ __forceinline__ void store_feat(FeatT *dst, float f);
-template <> __device__ __forceinline__ void store_feat<float>(float *dst, float f) { *dst = f; }
-template <> __device__ __forceinline__ void store_feat<__nv_bfloat16>(__nv_bfloat16 *dst, float f) { *dst = __float2bfloat16_rn(f); }
+// kPlanes bf16 planes of a feature row of kPlanes * 256 columns (masknet_fused.cuh: 1 = bf16 mode, 3 = hi | mid | lo of fp32 mode)
+template <typename FeatT, int kPlanes> __device__ __forceinline__ void store_feat(FeatT *dst, float f);
+template <> __device__ __forceinline__ void store_feat<float, 1>(float *dst, float f) { *dst = f; }
+template <> __device__ __forceinline__ void store_feat<__nv_bfloat16, 1>(__nv_bfloat16 *dst, float f) { *dst = __float2bfloat16_rn(f); }
+template <> __device__ __forceinline__ void store_feat<__nv_bfloat16, 3>(__nv_bfloat16 *dst, float f) {
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(f);
+        dst[pl * kBins] = b;
+        f -= __bfloat162float(b);
+    }
+}
 
 __device__ __forceinline__ float feature_of(float re, float im) {
     return kFeatGain * __logf((re * re + im * im) * kFeatPowerScale + kFeatEps) + kFeatBias;
@@ -33,8 +42,8 @@ __device__ __forceinline__ float feature_of(float re, float im) {
 // consecutive frames of every stream (the chunk the fused mask-estimator kernel then walks in one launch): frame t's first
 // half is frame t - 1 of the caller's buffer, or the stream's tail (the last frame of the previous chunk / call) for t = 0.
 // The tail itself is rewritten by backend_kernel, after every reader of this launch is done.
-// spec: [frames][slot_rows][512] fp32 packed (Re, Im of bins 0..255; the Im slot of bin 0 carries Re X[256]); feat: [frames][slot_rows][256].
-template <typename FeatT>
+// spec: [frames][slot_rows][512] fp32 packed (Re, Im of bins 0..255; the Im slot of bin 0 carries Re X[256]); feat: [frames][slot_rows][kPlanes * 256].
+template <typename FeatT, int kPlanes>
 __global__ void __launch_bounds__(kStftWarps * 32, kStftCtasPerSm)
 frontend_kernel(PcmView v, int n_streams, int frames, long long slot_rows, const int16_t *__restrict__ tail, float *__restrict__ spec,
                 FeatT *__restrict__ feat, const float2 *__restrict__ lane_tab) {
@@ -75,7 +84,7 @@ frontend_kernel(PcmView v, int n_streams, int frames, long long slot_rows, const
         //   E = (Z[k] + conj Z[256-k]) / 2,  O = (Z[k] - conj Z[256-k]) / 2i,  X[k] = E + W512^k O,  X[256-k] = conj(E - W512^k O)
         const size_t row = (size_t) t * slot_rows + s;
         float *spec_s = spec + row * kNfft;
-        FeatT *feat_s = feat + row * kBins;
+        FeatT *feat_s = feat + row * (kPlanes * kBins);
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const cpx zk = z[fft_reg_of_m(m)];
@@ -94,8 +103,8 @@ frontend_kernel(PcmView v, int n_streams, int frames, long long slot_rows, const
             }
             *reinterpret_cast<float2 *>(spec_s + 2 * ka) = make_float2(xa.x, xa.y);
             *reinterpret_cast<float2 *>(spec_s + 2 * kb) = make_float2(xb.x, xb.y);
-            store_feat<FeatT>(feat_s + ka, feature_of(xa.x, (m == 0 && lane0) ? 0.0f : xa.y));
-            store_feat<FeatT>(feat_s + kb, feature_of(xb.x, xb.y));
+            store_feat<FeatT, kPlanes>(feat_s + ka, feature_of(xa.x, (m == 0 && lane0) ? 0.0f : xa.y));
+            store_feat<FeatT, kPlanes>(feat_s + kb, feature_of(xb.x, xb.y));
         }
     }
 }

@@ -179,6 +179,16 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float *f) {
     return u;
 }
 
+// f[i] -= the bf16 value it was just rounded to (exact in fp32: Sterbenz): what remains is the next operand plane of fp32 mode
+__device__ __forceinline__ void sub_bf16x8(float *f, const uint4 &u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] -= __uint_as_float(w[i] << 16);
+        f[2 * i + 1] -= __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
 // Packs the three gate rows of each 64-unit tile contiguously: packed[(n * 3 + slot) * 64 + u][k] = W[gate * H + n * 64 + u][k]
 // with gate = order[slot] (PyTorch gate numbering r=0, z=1, n=2): W_ih uses n|r|z, W_hh uses r|z|n (see file header).
 __global__ void pack_gru_weights_kernel(const __nv_bfloat16 *__restrict__ W, __nv_bfloat16 *__restrict__ packed, int H, int g0,
@@ -196,6 +206,7 @@ __global__ void pack_gru_weights_kernel(const __nv_bfloat16 *__restrict__ W, __n
 struct TcModel {
     int H = 0, L = 0, Bp = 0;
     int tcap = 1, e_ring = 1;      // step slots of feat / mask, slots of the encoder-output ring e
+    int planes = 1;                // bf16 planes per activation operand: 1 (bf16 mode) or 3 (fp32 mode), masknet_fused.cuh
     const __nv_bfloat16 *enc_w = nullptr, *dec_w = nullptr, *wih[kMaxLayers] = {}, *whh[kMaxLayers] = {};
     const float *enc_b = nullptr, *dec_b = nullptr, *bih[kMaxLayers] = {}, *bhh[kMaxLayers] = {};
     __nv_bfloat16 *feat = nullptr, *e = nullptr, *hb[2] = {};

@@ -45,15 +45,16 @@ def frame_by_frame(model, n, pcm, precision="bf16"):
     return out, h
 
 
-@pytest.mark.parametrize("n_streams,chunk", [(300, 8), (70, 5), (300, 64)])
-def test_chunked_call_is_bit_identical_to_frame_by_frame(library_path, random_model_path, n_streams, chunk):
-    """37 frames in one call (chunks of `chunk` frames = steps per fused launch) == 37 calls of one frame, output and state."""
+@pytest.mark.parametrize("n_streams,chunk,precision", [(300, 8, "bf16"), (70, 5, "bf16"), (300, 64, "bf16"), (300, 8, "fp32"), (70, 64, "fp32")])
+def test_chunked_call_is_bit_identical_to_frame_by_frame(library_path, random_model_path, n_streams, chunk, precision):
+    """37 frames in one call (chunks of `chunk` frames = steps per fused launch) == 37 calls of one frame, output and state.
+    fp32 mode runs the same kernel with three bf16 operand planes (hi | mid | lo) per activation."""
     import torch
     frames = 37
     pcm = synth_pcm(n_streams, frames, seed=700 + n_streams)
-    ref, ref_h = frame_by_frame(random_model_path, n_streams, pcm)
+    ref, ref_h = frame_by_frame(random_model_path, n_streams, pcm, precision)
     with env(KOALA_CHUNK_FRAMES=chunk):
-        eng = kb.BatchKoala(n_streams, model_path=random_model_path, precision="bf16")
+        eng = kb.BatchKoala(n_streams, model_path=random_model_path, precision=precision)
     assert eng.chunk_frames == chunk
     # host buffers, stream-major
     out = eng.process(pcm)
@@ -148,3 +149,47 @@ def test_full_size_chunk_boundary(library_path, random_model_path):
     pick = [0, 1, 2, 3, 6, 7, 17, 63, 4096 + 9, 8191]
     ref = OracleBatch(OracleModel(random_model_path), len(pick), "bf16").process(np.ascontiguousarray(pcm[pick]), threads=8)
     assert np.abs(out[pick].astype(np.int32) - ref.astype(np.int32)).max() <= 1
+
+
+def test_fp32_tensor_core_path_against_cuda_core_path_and_oracle(library_path, random_model_path):
+    """fp32 mode has two implementations: the fused tensor-core kernel with every activation split into three bf16 planes (the
+    default whenever the hidden size fits its tiles) and the CUDA-core kernels (other hidden sizes; KOALA_FP32_CUDA_CORES=1).
+    Both must sit within the fp32 tolerances of the oracle -- and therefore of each other -- over a 200-frame state-carried run
+    fed in 64-frame calls."""
+    n, frames = 260, 200
+    pcm = synth_pcm(n, frames, seed=23)
+    ob = OracleBatch(OracleModel(random_model_path), n, "fp32")
+    ref = ob.process(pcm, threads=os.cpu_count() or 8)
+    outs = {}
+    for cores in (0, 1):
+        with env(KOALA_FP32_CUDA_CORES=cores):
+            eng = kb.BatchKoala(n, model_path=random_model_path, precision="fp32")
+        out = np.concatenate([eng.process(np.ascontiguousarray(pcm[:, t:t + 64])) for t in range(0, frames, 64)], axis=1)
+        # CUDA cores: 6 launches per frame; tensor cores: 3 per chunk (host buffers travel in chunks of a few frames)
+        assert (eng.kernel_launches == 6 * frames) if cores else (eng.kernel_launches % 3 == 0 and eng.kernel_launches <= 3 * frames // 4), eng.kernel_launches
+        assert np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= 1, cores
+        for l in range(2):
+            h = eng.debug_read(f"h{l}", (n, 512), np.float32)
+            np.testing.assert_allclose(h, np.stack([ob.stream(s).h[l] for s in range(n)]), atol=1e-4)
+        mask = eng.debug_read("mask", (n, 256), np.float32)
+        np.testing.assert_allclose(mask, np.stack([ob.stream(s).last_mask for s in range(n)]), rtol=1e-3, atol=1e-6)
+        outs[cores] = out
+        eng.delete()
+    assert np.abs(outs[0].astype(np.int32) - outs[1].astype(np.int32)).max() <= 1
+
+
+def test_fp32_hidden_size_outside_the_fused_tiles(library_path, tmp_path):
+    """H = 320 is not a multiple of 256: fp32 mode falls to the CUDA-core kernels (bf16 mode refuses such a model)."""
+    from koala_b200 import spec
+    path = str(tmp_path / "model_320_2.kpv")
+    spec.save_model(path, spec.random_model(seed=320, hidden=320, layers=2), hidden=320, layers=2)
+    n, frames = 37, 12
+    pcm = synth_pcm(n, frames, seed=320)
+    eng = kb.BatchKoala(n, model_path=path, precision="fp32")
+    out = eng.process(pcm)
+    assert eng.kernel_launches == 6 * frames
+    ref = OracleBatch(OracleModel(path), n, "fp32").process(pcm, threads=8)
+    assert np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= 1
+    eng.delete()
+    with pytest.raises(kb.KoalaError):
+        kb.BatchKoala(n, model_path=path, precision="bf16")
