@@ -83,7 +83,9 @@ PV_API void pv_log_disable(void);
 /* B independent streams resident on one GPU; stream s keeps the same state a pv_koala_t would. */
 typedef struct pv_koala_batch pv_koala_batch_t;
 
-/* precision: "bf16" (tcgen05 tensor-core mask estimator, default when NULL) or "fp32" (CUDA-core mask estimator). */
+/* precision: "bf16" (tcgen05 mask estimator, bf16 operands; default when NULL), "fp32" (the same kernel with every activation
+ * split into three bf16 planes; CUDA-core kernels when the hidden size is not a multiple of 256) or "int8" (the fixed-point
+ * variant: int8 weights x int16 activations on tcgen05 kind::i8, integer gates; SPEC.md section 6). */
 PV_API pv_status_t pv_koala_batch_init(const char *model_path, const char *device, int32_t num_streams, const char *precision,
                                        pv_koala_batch_t **object);
 PV_API void pv_koala_batch_delete(pv_koala_batch_t *object);

@@ -10,7 +10,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpv_koala_b200.so")
 SOURCES = ["engine.cu", "koala_abi.cu"]
-HEADERS = ["exports.map", "engine.h", "koala_common.cuh", "stft_kernels.cuh", "masknet_fp32.cuh", "tcgen05_common.cuh", "masknet_fused.cuh",
+HEADERS = ["exports.map", "engine.h", "koala_common.cuh", "stft_kernels.cuh", "masknet_fp32.cuh", "tcgen05_common.cuh", "masknet_fused.cuh", "masknet_i8.cuh",
            os.path.join("..", "..", "include", "pv_koala_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

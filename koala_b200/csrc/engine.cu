@@ -28,6 +28,7 @@
 #include "koala_common.cuh"
 #include "masknet_fp32.cuh"
 #include "masknet_fused.cuh"
+#include "masknet_i8.cuh"
 #include "stft_kernels.cuh"
 
 namespace koala {
@@ -143,6 +144,7 @@ struct Engine::Impl {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[kHostRing] = {}, ev_comp[kHostRing] = {}, ev_out[kHostOutRing] = {};
     FuPlan *fu = nullptr;        // tcgen05 path: packed weights, tensor maps and the tile schedule of the fused mask-estimator kernel
+    I8Plan *i8 = nullptr;        // fixed-point path: quantised weights, byte-plane activations and state, per-layer launches
     uint8_t *arena = nullptr;    // bf16 path: all per-stream state in one allocation
     size_t arena_bytes = 0;
     KernelProfiler *prof = nullptr;
@@ -229,7 +231,7 @@ static cudaError_t upload(std::vector<void *> &allocs, T **ptr, const std::vecto
 
 Status Engine::create(const ModelHost &model, int device, int num_streams, int precision, Engine **out,
                       std::vector<std::string> *errors) {
-    if (num_streams < 1 || (precision != kFp32 && precision != kBf16)) {
+    if (num_streams < 1 || (precision != kFp32 && precision != kBf16 && precision != kInt8)) {
         errors->push_back("Invalid number of streams or precision.");
         return kInvalidArgument;
     }
@@ -298,7 +300,7 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
         // fp32 mode runs on the tensor cores too when the model fits the fused kernel's tiles (three bf16 planes per operand);
         // KOALA_FP32_CUDA_CORES=1 keeps the CUDA-core kernels (comparison runs)
         const char *cc = getenv("KOALA_FP32_CUDA_CORES");
-        const bool fused = precision == kBf16 || (H % 256 == 0 && !(cc && cc[0] == '1'));
+        const bool fused = precision == kBf16 || (precision == kFp32 && H % 256 == 0 && !(cc && cc[0] == '1'));
         p->planes = precision == kFp32 ? 3 : 1;
         if (fused) {
             // frames per chunk: as many as keep feat + spec + mask under 512 MB, at most 64 (KOALA_CHUNK_FRAMES overrides)
@@ -317,7 +319,8 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             KCHECK(dev_alloc(p->allocs, &p->tail, Bp * kFrame));
             KCHECK(dev_alloc(p->allocs, &p->ola[0], Bp * kFrame));
             p->ola[1] = p->ola[0];
-            for (int i = 0; i < 2; i++) KCHECK(dev_alloc(p->allocs, &p->h[i], L * Bp * H));
+            if (precision == kFp32)
+                for (int i = 0; i < 2; i++) KCHECK(dev_alloc(p->allocs, &p->h[i], L * Bp * H));
         } else {
             // One arena for everything that survives a step: fp32 h (updated IN PLACE: a GRU tile reads and writes only its own
             // [256 streams x 64 units] slice; the other tiles read the bf16 copies, which stay ping-pong), both bf16 copies,
@@ -334,7 +337,13 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
             for (int i = 0; i < 2; i++) { p->ola[i] = (float *) a; a += ola_bytes; }
             p->tail = (int16_t *) a;
         }
-        if (!fused) {
+        if (precision == kInt8) {
+            std::string why;
+            if (!i8_plan_create(model, (int) Bp, p->mask, &p->i8, &why)) {
+                errors->push_back("Failed to set up the fixed-point mask path: " + why);
+                return kRuntimeError;
+            }
+        } else if (!fused) {
             KCHECK(dev_alloc(p->allocs, (float **) &p->feat, Bp * kBins));
             KCHECK(dev_alloc(p->allocs, (float **) &p->e, Bp * H));
         } else {
@@ -372,6 +381,7 @@ Engine::~Engine() {
     forget_fused_owner(device_, p_);
     if (p_->ev_order) cudaEventDestroy(p_->ev_order);
     if (p_->fu) fu_plan_destroy(p_->fu);
+    if (p_->i8) i8_plan_destroy(p_->i8);
     delete p_->prof;
     for (void *a : p_->allocs) cudaFree(a);
     for (int i = 0; i < kHostRing; i++) {
@@ -420,6 +430,23 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     const size_t LBH = (size_t) Bp * H;
     KernelProfiler *prof = p->prof;
     static const bool only_masknet = [] { const char *e = getenv("KOALA_B200_ONLY_MASKNET"); return e && e[0] == '1'; }();
+    if (p->i8) {           // fixed-point mode: analysis, encoder, GRU layers, decoder, synthesis -- one launch each per frame
+        const int grid = stft_grid_for(B, p->num_sms, p->stft_per_warp);
+        for (int t = 0; t < frames; t++) {
+            PcmView v{pcm, out, stride, out_stride, frame_stride, out_frame_stride, t};
+            if (prof) prof->begin(kKernFrontend, st);
+            launch_pdl(false, frontend_kernel<uint8_t, 2>, dim3(grid), dim3(kStftWarps * 32), 0, st, v, B, 1, (long long) Bp, p->tail, p->spec, p->i8->featp, p->tables);
+            if (prof) prof->end(st);
+            launches_ += 2 + i8_masknet_step(p->i8, p->parity, st, prof);
+            if (prof) prof->begin(kKernBackend, st);
+            launch_pdl(false, backend_kernel, dim3(grid), dim3(kStftWarps * 32), 0, st, v, B, 1, 1, (long long) Bp, p->spec, p->mask, p->ola[0], p->ola[0],
+                                                                            p->tail, p->tables);
+            if (prof) prof->end(st);
+            p->parity ^= 1;
+        }
+        KCHECK(cudaGetLastError());
+        return kSuccess;
+    }
     if (!p->fu) {          // fp32 mode, hidden size the fused kernel's tiles do not fit: CUDA-core kernels, frame by frame
         const int grid = stft_grid_for(B, p->num_sms, p->stft_per_warp);
         float *feat = (float *) p->feat, *e = (float *) p->e;
@@ -594,12 +621,13 @@ __global__ void reset_streams_kernel(const int32_t *__restrict__ ids, int n_ids,
         ola[(size_t) s * kFrame + k] = 0.0f;
         ola1[(size_t) s * kFrame + k] = 0.0f;
     }
-    for (int l = 0; l < L; l++)
-        for (int k = threadIdx.x; k < H; k += blockDim.x) {
-            const size_t idx = l * LBH + (size_t) s * H + k;
-            h0[idx] = 0.0f;
-            h1[idx] = 0.0f;
-        }
+    if (h0)
+        for (int l = 0; l < L; l++)
+            for (int k = threadIdx.x; k < H; k += blockDim.x) {
+                const size_t idx = l * LBH + (size_t) s * H + k;
+                h0[idx] = 0.0f;
+                h1[idx] = 0.0f;
+            }
     if (hb0)
         for (int l = 0; l < L; l++)
             for (int k = threadIdx.x; k < planes * H; k += blockDim.x) {
@@ -619,9 +647,11 @@ Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> 
     p->has_last = true;
     if (!stream_ids) {
         KCHECK(cudaMemsetAsync(p->tail, 0, Bp * kFrame * sizeof(int16_t), p->stream));
+        if (p->i8)
+            for (int i = 0; i < 2; i++) KCHECK(cudaMemsetAsync(p->i8->hp[i], 0, L * Bp * 2 * H, p->stream));
         for (int i = 0; i < 2; i++) {
             KCHECK(cudaMemsetAsync(p->ola[i], 0, Bp * kFrame * sizeof(float), p->stream));
-            KCHECK(cudaMemsetAsync(p->h[i], 0, L * Bp * H * sizeof(float), p->stream));
+            if (p->h[i]) KCHECK(cudaMemsetAsync(p->h[i], 0, L * Bp * H * sizeof(float), p->stream));
             if (p->hb[i]) KCHECK(cudaMemsetAsync(p->hb[i], 0, L * Bp * p->planes * H * sizeof(__nv_bfloat16), p->stream));
         }
     } else {
@@ -638,8 +668,10 @@ Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> 
             int32_t *d_ids = nullptr;
             KCHECK(cudaMalloc((void **) &d_ids, n * sizeof(int32_t)));
             cudaError_t e1 = cudaMemcpyAsync(d_ids, stream_ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream);
-            reset_streams_kernel<<<n, 128, 0, p->stream>>>(d_ids, n, n_, p->tail, p->ola[0], p->ola[1], p->h[0], p->h[1], p->hb[0], p->hb[1],
-                                                          (int) H, (int) L, Bp * H, p->planes);
+            // (fixed-point mode: the state is the two byte planes of h, 2 H bytes per stream and layer = H 2-byte elements)
+            __nv_bfloat16 *hb0 = p->i8 ? (__nv_bfloat16 *) p->i8->hp[0] : p->hb[0], *hb1 = p->i8 ? (__nv_bfloat16 *) p->i8->hp[1] : p->hb[1];
+            reset_streams_kernel<<<n, 128, 0, p->stream>>>(d_ids, n, n_, p->tail, p->ola[0], p->ola[1], p->h[0], p->h[1], hb0, hb1,
+                                                          (int) H, (int) L, Bp * H, p->i8 ? 1 : p->planes);
             cudaError_t e2 = cudaStreamSynchronize(p->stream);
             cudaFree(d_ids);
             KCHECK(e1);
@@ -694,6 +726,31 @@ Status Engine::debug_read(const char *name, void *dst, size_t bytes, std::vector
     const std::string nm(name ? name : "");
     // scratch of the last finished step: slot last_slot of the chunk buffers, ring slot (steps so far) % ring of e
     const size_t slot = p->fu ? (size_t) p->last_slot : 0;
+    if (p->i8) {
+        // fixed-point mode: activations and state are byte planes [rows][hi K | lo K]; hand out int16 ("feat" Q14, "e" Q12) and
+        // the state as fp32 = q / 32768 (exact), as the oracle keeps it
+        const bool is_h = nm.size() == 2 && nm[0] == 'h' && nm[1] >= '0' && nm[1] < '0' + p->L;
+        if (nm == "feat" || nm == "e" || is_h) {
+            const size_t cols = nm == "feat" ? (size_t) kBins : H, esz_out = is_h ? 4 : 2;
+            const uint8_t *base = nm == "feat" ? p->i8->featp : nm == "e" ? p->i8->ep : p->i8->hp[p->parity] + (size_t) (nm[1] - '0') * Bp * 2 * H;
+            if (bytes > B * cols * esz_out) {
+                if (errors) errors->push_back("Unknown tensor name or size too large.");
+                return kInvalidArgument;
+            }
+            const size_t rows = (bytes / esz_out + cols - 1) / cols;
+            std::vector<uint8_t> raw(rows * 2 * cols);
+            KCHECK(cudaMemcpy(raw.data(), base, raw.size(), cudaMemcpyDeviceToHost));
+            std::vector<uint8_t> outb(rows * cols * esz_out);
+            for (size_t r = 0; r < rows; r++)
+                for (size_t c = 0; c < cols; c++) {
+                    const int16_t q = (int16_t) (((int) (int8_t) raw[r * 2 * cols + c]) * 256 + raw[r * 2 * cols + cols + c]);
+                    if (is_h) { const float f = (float) q * (1.0f / 32768.0f); memcpy(&outb[(r * cols + c) * 4], &f, 4); }
+                    else memcpy(&outb[(r * cols + c) * 2], &q, 2);
+                }
+            memcpy(dst, outb.data(), bytes);
+            return kSuccess;
+        }
+    }
     if (p->fu && p->planes > 1 && (nm == "feat" || nm == "e")) {
         // fp32 mode on the tensor-core path keeps these as three bf16 planes per row: hand out their sum, the fp32 value
         const size_t cols = nm == "feat" ? (size_t) kBins : H, P = p->planes;

@@ -132,6 +132,7 @@ int precision_from(const char *s, bool *ok) {
     }
     if (strcmp(s, "bf16") == 0) return koala::kBf16;
     if (strcmp(s, "fp32") == 0) return koala::kFp32;
+    if (strcmp(s, "int8") == 0) return koala::kInt8;
     *ok = false;
     return koala::kBf16;
 }
@@ -230,7 +231,7 @@ PV_API pv_status_t pv_koala_init(const char *access_key, const char *model_path,
                                                  tag(kCodeGeneric, "Picovoice Error.")});
     bool ok;
     const int precision = precision_from(NULL, &ok);
-    if (!ok) return fail(PV_STATUS_INVALID_ARGUMENT, {tag(kCodeGeneric, "KOALA_B200_PRECISION must be `bf16` or `fp32`.")});
+    if (!ok) return fail(PV_STATUS_INVALID_ARGUMENT, {tag(kCodeGeneric, "KOALA_B200_PRECISION must be `bf16`, `fp32` or `int8`.")});
     Engine *eng = nullptr;
     pv_status_t st = create_engine(model_path, device, 1, precision, &eng);
     if (st != PV_STATUS_SUCCESS) return st;
@@ -321,7 +322,7 @@ PV_API pv_status_t pv_koala_batch_init(const char *model_path, const char *devic
     if (num_streams < 1) return fail(PV_STATUS_INVALID_ARGUMENT, {tag(kCodeGeneric, "`num_streams` must be positive.")});
     bool ok;
     const int prec = precision_from(precision, &ok);
-    if (!ok) return fail(PV_STATUS_INVALID_ARGUMENT, {tag(kCodeGeneric, "`precision` must be `bf16` or `fp32`.")});
+    if (!ok) return fail(PV_STATUS_INVALID_ARGUMENT, {tag(kCodeGeneric, "`precision` must be `bf16`, `fp32` or `int8`.")});
     Engine *eng = nullptr;
     pv_status_t st = create_engine(model_path, device, num_streams, prec, &eng);
     if (st != PV_STATUS_SUCCESS) return st;

@@ -23,7 +23,7 @@ constexpr float kFeatEps = 1e-6f;
 constexpr float kFeatGain = 0.125f;
 constexpr float kFeatBias = 0.25f;
 
-enum Precision : int { kFp32 = 0, kBf16 = 1 };
+enum Precision : int { kFp32 = 0, kBf16 = 1, kInt8 = 2 };   // kInt8: the fixed-point variant (SPEC.md section 6, masknet_i8.cuh)
 
 // kernel classes of one step, in launch order (per-class timing for bench.py's roofline object)
 // (kKernMasknet: the fused encoder -> GRU -> decoder kernel of the bf16 path; Enc / Gru / Dec: the fp32 path's separate kernels)

@@ -33,6 +33,13 @@ template <> __device__ __forceinline__ void store_feat<__nv_bfloat16, 3>(__nv_bf
     }
 }
 
+// fixed-point mode (masknet_i8.cuh): the feature as int16 Q14 (round to nearest even, saturating), hi byte plane | lo byte plane
+template <> __device__ __forceinline__ void store_feat<uint8_t, 2>(uint8_t *dst, float f) {
+    const int q = min(max(__float2int_rn(f * 16384.0f), -32768), 32767);
+    dst[0] = (uint8_t) ((q >> 8) & 255);
+    dst[kBins] = (uint8_t) (q & 255);
+}
+
 __device__ __forceinline__ float feature_of(float re, float im) {
     return kFeatGain * __logf((re * re + im * im) * kFeatPowerScale + kFeatEps) + kFeatBias;
 }

@@ -102,7 +102,7 @@ def main(argv=None) -> int:
     ap.add_argument('-o', '--output_paths', nargs='+', required=True)
     ap.add_argument('-m', '--model_path', default=None)
     ap.add_argument('-y', '--device', default='best')
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32', 'int8'])
     ap.add_argument('-l', '--library_path', default=None)
     args = ap.parse_args(argv)
     stats = enhance_files(args.input_paths, args.output_paths, model_path=args.model_path, device=args.device,

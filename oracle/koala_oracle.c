@@ -20,6 +20,12 @@
  * mode 0 ("fp32"): GEMM operands fp32 (weights are bf16-representable by construction).
  * mode 1 ("bf16"): every GEMM activation operand (features, encoder output, h) is rounded to bf16 (RNE) first;
  *                  accumulation, gates and the recurrent state stay fp32.
+ * mode 2 ("int8"): the fixed-point variant of SPEC.md section 6 (the reference engine's numeric style, SURVEY.md F4: int8
+ *                  weights x int16 activations -> int32, table-driven gates): weights quantised per output row at load
+ *                  time, int16 activations (features Q14, encoder output Q12, state Q15), int32 accumulation, 64-bit
+ *                  requantisation multipliers, sigmoid / tanh from a 2049-entry table with linear interpolation.  Pure
+ *                  integer arithmetic between the quantised features and the mask, so the CUDA path must match it BIT FOR
+ *                  BIT there; analysis and synthesis stay fp32 as in the other modes.
  */
 #include <math.h>
 #include <pthread.h>
@@ -43,7 +49,120 @@ typedef struct ko_model {
     float *dec_wt, *dec_b;                 /* [H][bins], [bins] */
     float window[NFFT];
     float tw_re[NFFT / 2], tw_im[NFFT / 2]; /* exp(-2 pi i k / 512) */
+    /* fixed-point variant (SPEC.md section 6), built on first use of mode 2 */
+    struct ko_qmodel *q;
 } ko_model_t;
+
+/* ---------------------------------------------------------------- fixed-point model (SPEC.md section 6) */
+enum { QF = 14, QE = 12, QH = 15, QP = 12, SIG_N = 2048 };
+typedef struct ko_qmodel {
+    int8_t *enc_q;                          /* [H][256] */
+    int32_t *enc_m, *enc_b;                 /* [H] multiplier, bias (Q12) */
+    int8_t *ih_q[MAXL], *hh_q[MAXL];        /* [3H][H], PyTorch row order r | z | n */
+    int32_t *g_m[MAXL], *g_b[MAXL];         /* [4][H]: r, z, n_x, n_h */
+    int8_t *dec_q;                          /* [256][H] */
+    int32_t *dec_m, *dec_b;                 /* [256] */
+    int16_t sig[SIG_N + 1];
+} ko_qmodel_t;
+
+static float row_scale(float maxabs) { return maxabs > 0.0f ? maxabs / 127.0f : 1.0f; }
+static int8_t quant_w(float w, float s) {
+    float q = rintf(w / s);
+    if (q > 127.0f) q = 127.0f;
+    if (q < -127.0f) q = -127.0f;
+    return (int8_t) q;
+}
+static int32_t quant_mult(float s, int q_in) {
+    double m = (double) s * ldexp(1.0, QP - q_in + 31);
+    long long v = llrint(m);
+    if (v > 2147483647LL) v = 2147483647LL;
+    return (int32_t) v;
+}
+static int32_t quant_bias(float b) { return (int32_t) lrintf(b * 4096.0f); }
+static float maxabs_col(const float *wt, int K, int N, int n, float c) {   /* max_k |c * W[n][k]| from the transposed copy Wt[k][n] */
+    float m = 0.0f;
+    for (int k = 0; k < K; k++) {
+        float v = fabsf(c * wt[(size_t) k * N + n]);
+        if (v > m) m = v;
+    }
+    return m;
+}
+
+static void qmodel_free(ko_qmodel_t *q) {
+    if (!q) return;
+    free(q->enc_q); free(q->enc_m); free(q->enc_b); free(q->dec_q); free(q->dec_m); free(q->dec_b);
+    for (int l = 0; l < MAXL; l++) { free(q->ih_q[l]); free(q->hh_q[l]); free(q->g_m[l]); free(q->g_b[l]); }
+    free(q);
+}
+
+static ko_qmodel_t *qmodel_build(const ko_model_t *m) {
+    const int H = m->hidden;
+    ko_qmodel_t *q = (ko_qmodel_t *) calloc(1, sizeof(*q));
+    q->enc_q = (int8_t *) malloc((size_t) H * BINS);
+    q->enc_m = (int32_t *) malloc(sizeof(int32_t) * H);
+    q->enc_b = (int32_t *) malloc(sizeof(int32_t) * H);
+    for (int n = 0; n < H; n++) {
+        float s = row_scale(maxabs_col(m->enc_wt, BINS, H, n, 1.0f));
+        for (int k = 0; k < BINS; k++) q->enc_q[(size_t) n * BINS + k] = quant_w(m->enc_wt[(size_t) k * H + n], s);
+        q->enc_m[n] = quant_mult(s, QF);
+        q->enc_b[n] = quant_bias(m->enc_b[n]);
+    }
+    for (int l = 0; l < m->layers; l++) {
+        const float c = l == 0 ? 8.0f : 1.0f;   /* 2^(QH - Q of the layer input): e is Q12, h is Q15 */
+        const float *wi = m->wih_t[l], *wh = m->whh_t[l];
+        q->ih_q[l] = (int8_t *) malloc((size_t) 3 * H * H);
+        q->hh_q[l] = (int8_t *) malloc((size_t) 3 * H * H);
+        q->g_m[l] = (int32_t *) malloc(sizeof(int32_t) * 4 * H);
+        q->g_b[l] = (int32_t *) malloc(sizeof(int32_t) * 4 * H);
+        for (int j = 0; j < H; j++) {
+            for (int g = 0; g < 2; g++) {       /* r, z: one scale for the x and the h half of the sum */
+                const int n = g * H + j;
+                float a = maxabs_col(wi, H, 3 * H, n, c), b = maxabs_col(wh, H, 3 * H, n, 1.0f);
+                float s = row_scale(a > b ? a : b);
+                for (int k = 0; k < H; k++) {
+                    q->ih_q[l][(size_t) n * H + k] = quant_w(c * wi[(size_t) k * 3 * H + n], s);
+                    q->hh_q[l][(size_t) n * H + k] = quant_w(wh[(size_t) k * 3 * H + n], s);
+                }
+                q->g_m[l][g * H + j] = quant_mult(s, QH);
+                q->g_b[l][g * H + j] = quant_bias(m->bih[l][n] + m->bhh[l][n]);
+            }
+            const int n = 2 * H + j;
+            float sx = row_scale(maxabs_col(wi, H, 3 * H, n, c)), sh = row_scale(maxabs_col(wh, H, 3 * H, n, 1.0f));
+            for (int k = 0; k < H; k++) {
+                q->ih_q[l][(size_t) n * H + k] = quant_w(c * wi[(size_t) k * 3 * H + n], sx);
+                q->hh_q[l][(size_t) n * H + k] = quant_w(wh[(size_t) k * 3 * H + n], sh);
+            }
+            q->g_m[l][2 * H + j] = quant_mult(sx, QH);
+            q->g_b[l][2 * H + j] = quant_bias(m->bih[l][n]);
+            q->g_m[l][3 * H + j] = quant_mult(sh, QH);
+            q->g_b[l][3 * H + j] = quant_bias(m->bhh[l][n]);
+        }
+    }
+    q->dec_q = (int8_t *) malloc((size_t) BINS * H);
+    q->dec_m = (int32_t *) malloc(sizeof(int32_t) * BINS);
+    q->dec_b = (int32_t *) malloc(sizeof(int32_t) * BINS);
+    for (int n = 0; n < BINS; n++) {
+        float s = row_scale(maxabs_col(m->dec_wt, H, BINS, n, 1.0f));
+        for (int k = 0; k < H; k++) q->dec_q[(size_t) n * H + k] = quant_w(m->dec_wt[(size_t) k * BINS + n], s);
+        q->dec_m[n] = quant_mult(s, QH);
+        q->dec_b[n] = quant_bias(m->dec_b[n]);
+    }
+    for (int i = 0; i <= SIG_N; i++) q->sig[i] = (int16_t) lrint(32768.0 / (1.0 + exp(-(double) (i - SIG_N / 2) / 128.0)));
+    return q;
+}
+
+static inline int32_t requant(int32_t acc, int32_t mult) { return (int32_t) (((int64_t) acc * mult + ((int64_t) 1 << 30)) >> 31); }
+static inline int32_t sig_q15(const int16_t *t, int32_t p) {        /* Q12 in, Q15 out */
+    int32_t x = (p < -32768 ? -32768 : p > 32767 ? 32767 : p) + 32768;
+    int32_t i = x >> 5, f = x & 31;
+    return t[i] + ((((int32_t) t[i + 1] - t[i]) * f + 16) >> 5);
+}
+static inline int32_t tanh_q15(const int16_t *t, int32_t a) { return 2 * sig_q15(t, a < -16384 ? -32768 : a > 16383 ? 32767 : 2 * a) - 32768; }
+static inline int32_t dot_q(const int8_t *w, const int16_t *x, int K) {   /* exact sum, reduced mod 2^32 like the int32 accumulator */
+    int64_t s = 0;
+    for (int k = 0; k < K; k++) s += (int32_t) w[k] * (int32_t) x[k];
+    return (int32_t) (uint32_t) s;
+}
 
 /* ---------------------------------------------------------------- model file (format: koala_b200/spec.py) */
 static uint32_t crc32_bytes(const uint8_t *p, size_t n) {
@@ -98,6 +217,7 @@ KO_API void ko_model_free(ko_model_t *m) {
     if (!m) return;
     free(m->enc_wt); free(m->enc_b); free(m->dec_wt); free(m->dec_b);
     for (int l = 0; l < MAXL; l++) { free(m->wih_t[l]); free(m->whh_t[l]); free(m->bih[l]); free(m->bhh[l]); }
+    qmodel_free(m->q);
     free(m);
 }
 
@@ -143,6 +263,7 @@ KO_API int ko_model_load(const char *path, ko_model_t **out) {
         m->tw_re[k] = (float) cos(a);
         m->tw_im[k] = (float) sin(a);
     }
+    m->q = qmodel_build(m);
     *out = m;
     return 0;
 }
@@ -307,7 +428,59 @@ static void masknet_block(ko_stream_t **st, int S, const float *feat, float *mas
 
 static size_t scratch_floats(int H) { return (size_t) 8 * H * 3 + (size_t) 8 * 3 * H * 2; }
 
+/* fixed-point mask network of one stream (SPEC.md section 6): fq[256] int16 Q14 -> mask; the state is kept as h = q / 32768 */
+KO_API void ko_masknet_q(ko_stream_t *s, const int16_t *fq, float *mask) {
+    const ko_model_t *m = s->m;
+    const ko_qmodel_t *q = m->q;
+    const int H = m->hidden;
+    int16_t *x = (int16_t *) malloc(sizeof(int16_t) * 2 * H), *hq = x + H;
+    for (int n = 0; n < H; n++) {
+        int32_t p = requant(dot_q(q->enc_q + (size_t) n * BINS, fq, BINS), q->enc_m[n]) + q->enc_b[n];
+        x[n] = (int16_t) (p < 0 ? 0 : p > 32767 ? 32767 : p);
+    }
+    for (int l = 0; l < m->layers; l++) {
+        float *h = s->h + l * H;
+        const int32_t *gm = q->g_m[l], *gb = q->g_b[l];
+        for (int j = 0; j < H; j++) hq[j] = (int16_t) lrintf(h[j] * 32768.0f);
+        for (int j = 0; j < H; j++) {
+            const int8_t *wi = q->ih_q[l], *wh = q->hh_q[l];
+            int32_t ar = (int32_t) ((uint32_t) dot_q(wi + (size_t) j * H, x, H) + (uint32_t) dot_q(wh + (size_t) j * H, hq, H));
+            int32_t az = (int32_t) ((uint32_t) dot_q(wi + (size_t) (H + j) * H, x, H) + (uint32_t) dot_q(wh + (size_t) (H + j) * H, hq, H));
+            int32_t r = sig_q15(q->sig, requant(ar, gm[j]) + gb[j]);
+            int32_t z = sig_q15(q->sig, requant(az, gm[H + j]) + gb[H + j]);
+            int32_t pnx = requant(dot_q(wi + (size_t) (2 * H + j) * H, x, H), gm[2 * H + j]) + gb[2 * H + j];
+            int32_t pnh = requant(dot_q(wh + (size_t) (2 * H + j) * H, hq, H), gm[3 * H + j]) + gb[3 * H + j];
+            int32_t a = pnx + (int32_t) (((int64_t) r * pnh + (1 << 14)) >> 15);
+            int32_t nn = tanh_q15(q->sig, a);
+            int32_t hn = nn + (int32_t) (((int64_t) z * (hq[j] - nn) + (1 << 14)) >> 15);
+            hn = hn < -32767 ? -32767 : hn > 32767 ? 32767 : hn;
+            h[j] = (float) hn * (1.0f / 32768.0f);
+        }
+        for (int j = 0; j < H; j++) x[j] = (int16_t) lrintf(h[j] * 32768.0f);
+    }
+    for (int n = 0; n < BINS; n++) {
+        int32_t p = requant(dot_q(q->dec_q + (size_t) n * H, x, H), q->dec_m[n]) + q->dec_b[n];
+        mask[n] = (float) sig_q15(q->sig, p) * (1.0f / 32768.0f);
+    }
+    free(x);
+    memcpy(s->last_mask, mask, sizeof(float) * BINS);
+}
+
+/* features -> int16 Q14, round to nearest even, saturating */
+KO_API void ko_quantize_feat(const float *feat, int16_t *fq) {
+    for (int k = 0; k < BINS; k++) {
+        long v = lrintf(feat[k] * 16384.0f);
+        fq[k] = (int16_t) (v < -32768 ? -32768 : v > 32767 ? 32767 : v);
+    }
+}
+
 KO_API void ko_masknet(ko_stream_t *s, const float *feat, float *mask) {
+    if (s->mode == 2) {
+        int16_t fq[BINS];
+        ko_quantize_feat(feat, fq);
+        ko_masknet_q(s, fq, mask);
+        return;
+    }
     float *scratch = (float *) malloc(sizeof(float) * scratch_floats(s->m->hidden));
     masknet_block(&s, 1, feat, mask, scratch);
     free(scratch);
@@ -388,7 +561,8 @@ static void *batch_worker(void *arg) {
             int S = j->s1 - s0 < 8 ? j->s1 - s0 : 8;
             for (int s = 0; s < S; s++)
                 ko_frontend(j->b->st[s0 + s], j->pcm + ((size_t) (s0 + s) * j->stride + (size_t) t * FRAME), spec[s], feat + s * BINS);
-            masknet_block(j->b->st + s0, S, feat, mask, scratch);
+            if (j->b->mode == 2) for (int s = 0; s < S; s++) ko_masknet(j->b->st[s0 + s], feat + s * BINS, mask + s * BINS);
+            else masknet_block(j->b->st + s0, S, feat, mask, scratch);
             for (int s = 0; s < S; s++)
                 ko_backend(j->b->st[s0 + s], spec[s], mask + s * BINS, j->out + ((size_t) (s0 + s) * j->stride + (size_t) t * FRAME));
         }

@@ -42,6 +42,8 @@ def _load():
         lib.ko_stream_process.argtypes = [vp, i16p, i16p]; lib.ko_stream_process.restype = None
         lib.ko_frontend.argtypes = [vp, i16p, f32p, f32p]; lib.ko_frontend.restype = None
         lib.ko_masknet.argtypes = [vp, f32p, f32p]; lib.ko_masknet.restype = None
+        lib.ko_masknet_q.argtypes = [vp, i16p, f32p]; lib.ko_masknet_q.restype = None
+        lib.ko_quantize_feat.argtypes = [f32p, i16p]; lib.ko_quantize_feat.restype = None
         lib.ko_backend.argtypes = [vp, f32p, f32p, i16p]; lib.ko_backend.restype = None
         lib.ko_stream_h.argtypes = [vp]; lib.ko_stream_h.restype = f32p
         lib.ko_stream_ola.argtypes = [vp]; lib.ko_stream_ola.restype = f32p
@@ -65,7 +67,7 @@ def _f32(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
-MODES = {"fp32": 0, "bf16": 1}
+MODES = {"fp32": 0, "bf16": 1, "int8": 2}
 
 
 class OracleModel:
@@ -148,6 +150,13 @@ class Oracle(_StreamView):
         feat = np.ascontiguousarray(feat, dtype=np.float32)
         mask = np.empty(BINS, np.float32)
         self._lib.ko_masknet(self._s, _f32(feat), _f32(mask))
+        return mask
+
+    def masknet_q(self, feat_q):
+        """Fixed-point mode only: the integer mask network on already quantised features (int16 Q14)."""
+        feat_q = np.ascontiguousarray(feat_q, dtype=np.int16)
+        mask = np.empty(BINS, np.float32)
+        self._lib.ko_masknet_q(self._s, _i16(feat_q), _f32(mask))
         return mask
 
     def backend(self, spec, mask):

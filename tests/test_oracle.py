@@ -117,17 +117,17 @@ def _energy_test(model, mode, input_pcm, reference_pcm, tolerance=0.02):
     assert worst < tolerance, worst
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "int8"])
 def test_reference_behaviour_pure_speech(shipped, test_pcm, mode):
     _energy_test(shipped, mode, test_pcm, test_pcm)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "int8"])
 def test_reference_behaviour_pure_noise(shipped, noise_pcm, mode):
     _energy_test(shipped, mode, noise_pcm, None)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "int8"])
 def test_reference_behaviour_mixed(shipped, test_pcm, noise_pcm, mode):
     noisy = np.clip(test_pcm.astype(np.int32) + noise_pcm.astype(np.int32), -32768, 32767).astype(np.int16)
     _energy_test(shipped, mode, noisy, test_pcm)
@@ -137,3 +137,38 @@ def test_fixture_facts(test_pcm, noise_pcm):
     """both fixtures are 93 680 samples = 365 full frames + 240."""
     assert len(test_pcm) == len(noise_pcm) == 93680
     assert len(test_pcm) // 256 == 365
+
+
+# ---------------------------------------------------------------- fixed-point mode (SPEC.md section 6)
+def test_fixed_point_c_oracle_matches_numpy_restatement_bit_for_bit(random_model_path):
+    """Two independent restatements of the integer mask network (C, mode 2; numpy int64) from the same quantised features:
+    the Q15 mask and the Q15 state must be identical after every step."""
+    from koala_b200 import spec
+    from oracle.numpy_oracle import NumpyFixedPoint
+    model = spec.load_model(random_model_path)
+    om = OracleModel(random_model_path)
+    o, nq = Oracle(om, "int8"), NumpyFixedPoint(model)
+    pcm = synth_pcm(1, 12, seed=3)[0]
+    for t in range(12):
+        _, feat = o.frontend(pcm[t])
+        fq = NumpyFixedPoint.quantize_feat(feat)
+        mask = o.masknet_q(fq.astype(np.int16))
+        mq = nq.masknet_q(fq)
+        assert (np.rint(mask * 32768.0).astype(np.int64) == mq).all(), t
+        assert (np.rint(o.h * 32768.0).astype(np.int64) == nq.hq).all(), t
+    assert 0 < mq.min() and mq.max() <= 32768
+
+
+def test_fixed_point_mode_tracks_fp32_mode(random_model_path, shipped_model_path):
+    """The fixed-point variant is the same network with int8 weights and int16 activations: on the fixture speech its mask stays within
+    2e-2 of the fp32 mode's and the enhanced samples within a few LSB; reset makes it repeat bit for bit."""
+    pcm = synth_pcm(1, 40, seed=9)[0]
+    for path in (random_model_path, shipped_model_path):
+        om = OracleModel(path)
+        a, b = Oracle(om, "fp32"), Oracle(om, "int8")
+        oa = np.stack([a.process(f) for f in pcm])
+        ob = np.stack([b.process(f) for f in pcm])
+        assert np.abs(a.last_mask - b.last_mask).max() < 2e-2
+        assert np.abs(oa.astype(np.int32) - ob.astype(np.int32)).max() <= 8
+        b.reset()
+        assert (np.stack([b.process(f) for f in pcm]) == ob).all()
