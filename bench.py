@@ -40,9 +40,12 @@ WORKLOADS = {
     "cfg2_256_fp32": dict(streams=256, precision="fp32", frames_per_call=64,
                           desc="BASELINE configs[1]: 256 concurrent streams, 1xB200, fp32 mask path (tcgen05 with every activation split into "
                                "three bf16 planes, fp32 accumulation), fed 64 frames per process() call"),
-    "cfg5_128_per_gpu_bf16": dict(streams=128, precision="bf16", frames_per_call=64,
-                                  desc="BASELINE configs[4] per-GPU partition: 128 streams/GPU (1024 over 8 GPUs), 10-minute clips fed in "
-                                       "64-frame process() calls with the state carried across calls"),
+    "cfg5_128_per_gpu_bf16": dict(streams=128, precision="bf16", frames_per_call=64, steps=37504,
+                                  desc="BASELINE configs[4] per-GPU partition: 128 streams/GPU (1024 over 8 GPUs), 10-minute clips (37 504 frames) "
+                                       "fed in 64-frame process() calls with the state carried across all 586 calls"),
+    "fixed_point_4096_int8": dict(streams=4096, precision="int8", frames_per_call=16,
+                                  desc="SURVEY section 8f row 3: fixed-point variant (int8 weights x int16 activations on tcgen05 kind::i8, integer "
+                                       "gates; SPEC.md section 6), 4096 concurrent streams, 1xB200"),
 }
 DEFAULT_WORKLOAD = "cfg4_8192_per_gpu_bf16"
 FRAME = 256
@@ -410,12 +413,15 @@ def roofline_of(name, streams, precision, prof, prof_steps, timed_seconds, peaks
     else:
         peak, src = (1590.0, "fallback 1.59 PFLOP/s burst (B200_PROFILING.md), of fallback") if burst else (1400.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md), of fallback")
     achieved = dom_flops / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 if dom_n else None
+    if precision == "int8":      # integer tensor pipe: no measured peak in MEASURED_PEAKS.json to divide by
+        peak, src = None, "no measured int8 tensor peak available (MEASURED_PEAKS.json has bf16 only); achieved is in Tera integer op/s"
     traffic, traffic_src = ncu_traffic(name) if streams == WORKLOADS[name]["streams"] else (None, "stream count overridden")
     kernel = ("tc_fused_kernel (encoder + GRU layers + decoder GEMMs, all streams" + ("" if prof_steps == dom_n else f", {prof_steps // max(dom_n, 1)} steps per launch") +
               (", fp32 operands as three bf16 planes: 3x the algorithmic flops are executed" if precision == "fp32" else "") + ")") if fused \
-        else "gru_fp32_kernel (CUDA-core FMA GRU layer)"
+        else ("i8_layer_kernel<GRU> (one GRU layer, tcgen05 kind::i8, hi and lo byte planes: 2x the algorithmic multiply-adds are executed, "
+              "plus a quarter of zero rows)" if precision == "int8" else "gru_fp32_kernel (CUDA-core FMA GRU layer)")
     r = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": src,
+         "frac": (achieved / peak) if achieved and peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": src,
          "avg_launch_ms": dom_ms / max(dom_n, 1), "algorithmic_flops_per_launch": dom_flops, "kernel_share_of_step": shares,
          "note": "launch duration from CUDA events bracketing the kernel; bracketing disables the dependent-launch overlap with the "
                  "neighbouring kernels, so the bracketed durations sum to more than ms_per_step"}
@@ -550,6 +556,8 @@ def main():
                 r = Runner(name, ow["streams"], model, local_rank, 1)
                 r.setup_ring(args.ring_frames, seed=0x4B4F414C)
                 o_steps = max(ow["frames_per_call"] * 4, min(args.steps, 512))
+                if args.steps >= 512 and ow.get("steps"):
+                    o_steps = ow["steps"]        # the config's own length (configs[4]: a 10-minute clip per stream)
                 o_ms, o_launches, o_calls, _ = r.timed(o_steps, max(args.warmup, ow["frames_per_call"]))
                 o_prof_steps = max(ow["frames_per_call"], 64)
                 o_prof = r.profile(o_steps, o_prof_steps)
@@ -571,7 +579,7 @@ def main():
         roofline = roofline_of(args.workload, streams, precision, prof, prof_steps, ms * 1e-3, peaks)
         step_prof_ms = sum(v[0] for v in prof.values()) / max(prof_steps, 1)
         step_peak = roofline["peak"]
-        roofline["step_tensor_frac"] = (value / world) * FLOPS_PER_FRAME / 1e12 / step_peak
+        roofline["step_tensor_frac"] = (value / world) * FLOPS_PER_FRAME / 1e12 / step_peak if step_peak else None
         roofline["step_hbm_frac"] = (value / world) * BYTES_PER_FRAME / 1e9 / (peaks.get("hbm_gbs", 6650.0))
         line = {
             "metric": "enhanced_frames_per_second", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,

@@ -133,7 +133,7 @@ def test_no_gpu_means_loud_failure_not_fallback(lib, random_model_path):
         _stack(lib)
     b = c_void_p()
     assert lib.pv_koala_batch_init(random_model_path.encode(), b"best", 0, b"bf16", byref(b)) == 3
-    assert lib.pv_koala_batch_init(random_model_path.encode(), b"best", 8, b"int8", byref(b)) == 3
+    assert lib.pv_koala_batch_init(random_model_path.encode(), b"best", 8, b"fp64", byref(b)) == 3
     _stack(lib)
 
 
