@@ -172,3 +172,50 @@ def test_fixed_point_mode_tracks_fp32_mode(random_model_path, shipped_model_path
         assert np.abs(oa.astype(np.int32) - ob.astype(np.int32)).max() <= 8
         b.reset()
         assert (np.stack([b.process(f) for f in pcm]) == ob).all()
+
+
+# ---------------------------------------------------------------- held-out behaviour of the shipped weights
+def _speechlike(n, rng):
+    t = np.arange(n) / 16000.0
+    f0 = rng.uniform(90, 260) * (1 + 0.05 * np.sin(2 * np.pi * rng.uniform(1, 3) * t))
+    ph = 2 * np.pi * np.cumsum(f0) / 16000.0
+    s = sum(np.sin(k * ph + rng.uniform(0, 6.28)) / k ** rng.uniform(0.8, 1.6) for k in range(1, 14))
+    s = s * np.clip(np.sin(2 * np.pi * rng.uniform(2.5, 5) * t + rng.uniform(0, 6.28)), 0, None) ** 1.5      # syllables with pauses
+    return s / (np.sqrt(np.mean(s ** 2)) + 1e-9)
+
+
+def _si_snr_db(sig, ref):
+    a = np.dot(sig, ref) / np.dot(ref, ref)
+    e = sig - a * ref
+    return 10 * np.log10(np.dot(a * ref, a * ref) / np.dot(e, e))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "int8"])
+def test_shipped_weights_denoise_signals_they_were_not_trained_on(shipped_model_path, mode):
+    """The reference's behavioural tests run on two fixture WAVs that tools/train_weights.py also trains on, so by themselves they say
+    nothing about other input.  Held-out check: seeded speech-like signals (gliding harmonic stacks with syllabic pauses,
+    a generator the trainer does not share) in white and pink noise at 0 / 5 / 10 dB: the scale-invariant SNR against the clean signal
+    must rise by at least 5 dB (measured: +8 to +11 dB).  Known limit, recorded in SPEC.md section 5: noise confined to the speech band
+    (low-passed at 1.3 kHz) is NOT removed by these weights."""
+    rng = np.random.default_rng(12345)
+    n = 256 * 200
+    cases, clean = [], []
+    for kind in ("white", "pink"):
+        for snr in (0, 5, 10):
+            s = _speechlike(n, rng) * 2000
+            w = rng.standard_normal(n)
+            if kind == "pink":
+                W = np.fft.rfft(w)
+                f = np.arange(len(W), dtype=np.float64)
+                f[0] = 1
+                w = np.fft.irfft(W / np.sqrt(f), n)
+            w = w / np.sqrt(np.mean(w ** 2)) * 2000 / 10 ** (snr / 20)
+            cases.append(np.clip(np.rint(s + w), -32768, 32767).astype(np.int16))
+            clean.append(s)
+    pcm = np.stack(cases).reshape(len(cases), -1, 256)
+    out = OracleBatch(OracleModel(shipped_model_path), len(cases), mode).process(pcm, threads=8).reshape(len(cases), -1).astype(np.float64)
+    skip = 256 * 20
+    for i in range(len(cases)):
+        c, y, x = clean[i][skip:-256], out[i][256 + skip:], pcm[i].reshape(-1)[skip:-256].astype(np.float64)      # output is delayed by 256 samples
+        gain = _si_snr_db(y, c) - _si_snr_db(x, c)
+        assert gain > 5.0, (i, gain)
