@@ -534,13 +534,18 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
     if (frames == 0) return kSuccess;
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
-    static const int chunk_env = [] { const char *e = getenv("KOALA_HOST_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : kHostChunkFrames; }();
+    const int chunk_forced = [] { const char *e = getenv("KOALA_HOST_CHUNK"); return e ? std::max(0, atoi(e)) : 0; }();      // tests / tuning: exactly this many frames per input chunk
     static const int out_env = [] { const char *e = getenv("KOALA_HOST_OUT_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : kHostOutFrames; }();
-    const int chunk_frames = time_major ? kHostChunkFramesTm : chunk_env;
+    // Small batches: a chunk of a few frames is a few hundred KB and the call becomes bound by the host's per-chunk work (two copies,
+    // three launches, four events: ~40 us) -- scale the chunk to ~4 MiB of PCM, up to what one fused launch walks (128 streams: 64 frames)
+    const int by_bytes = (int) std::min<size_t>((size_t) std::max(p->tcap, 1), ((size_t) 4 << 20) / ((size_t) n_ * kFrame * sizeof(int16_t)));
+    const int chunk_frames = chunk_forced > 0 ? chunk_forced : std::max(time_major ? kHostChunkFramesTm : kHostChunkFrames, by_bytes);
     const int Tc = frames < chunk_frames ? frames : chunk_frames;                 // frames per input chunk
     const int per_block = (time_major || frames < kHostBlockMinFrames) ? 1 : std::max(1, std::min(out_env, frames) / Tc);   // input chunks per output block
     const int To = per_block * Tc;                                                // frames per output block
-    if ((size_t) Tc > p->staging_frames || (size_t) To > p->staging_out_frames) {
+    // staging is sized for the layout's full chunk / block, not for this call's length: a short call must not make the next long one reallocate
+    const int need_in = chunk_frames, need_out = std::max(To, (time_major ? 1 : std::max(1, out_env / chunk_frames)) * chunk_frames);
+    if ((size_t) need_in > p->staging_frames || (size_t) need_out > p->staging_out_frames) {
         for (int i = 0; i < kHostRing; i++) {
             if (p->d_in[i]) cudaFree(p->d_in[i]);
             p->d_in[i] = nullptr;
@@ -550,10 +555,10 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
             p->d_out[i] = nullptr;
         }
         p->staging_frames = p->staging_out_frames = 0;
-        for (int i = 0; i < kHostRing; i++) KCHECK(cudaMalloc((void **) &p->d_in[i], (size_t) n_ * Tc * kFrame * sizeof(int16_t)));
-        for (int i = 0; i < kHostOutRing; i++) KCHECK(cudaMalloc((void **) &p->d_out[i], (size_t) n_ * To * kFrame * sizeof(int16_t)));
-        p->staging_frames = Tc;
-        p->staging_out_frames = To;
+        for (int i = 0; i < kHostRing; i++) KCHECK(cudaMalloc((void **) &p->d_in[i], (size_t) n_ * need_in * kFrame * sizeof(int16_t)));
+        for (int i = 0; i < kHostOutRing; i++) KCHECK(cudaMalloc((void **) &p->d_out[i], (size_t) n_ * need_out * kFrame * sizeof(int16_t)));
+        p->staging_frames = need_in;
+        p->staging_out_frames = need_out;
     }
     if (!p->copy_in) {
         KCHECK(cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking));

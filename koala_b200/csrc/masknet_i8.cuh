@@ -39,7 +39,7 @@ constexpr int kI8Threads = 192;
 constexpr int kI8Units = 32;                              // GRU units per tile
 constexpr int kI8SigN = 2048;                             // sigmoid table intervals over [-8, 8)
 constexpr int kI8SigBytes = (kI8SigN + 1) * 2 + 14;       // padded to 16 bytes
-constexpr int kI8SmemBytes = 1024 + kI8Stages * kI8StageBytes + kI8SigBytes + 128;
+constexpr int kI8SmemBytes = 1024 + kI8Stages * kI8StageBytes + kI8SigBytes + 2 * kI8Tile * 4 + 128;
 constexpr int kQF = 14, kQE = 12, kQH = 15, kQP = 12;     // Q formats: features, encoder output, state, pre-activations
 
 enum I8Mode : int { kI8Enc = 0, kI8Gru = 1, kI8Dec = 2 };
@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 1023) & ~(uintptr_t) 1023);
     uint8_t *tail = smem + kI8Stages * kI8StageBytes;
     int16_t *s_sig = reinterpret_cast<int16_t *>(tail);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tail + kI8SigBytes);
+    int32_t *s_mult = reinterpret_cast<int32_t *>(tail + kI8SigBytes), *s_bias = s_mult + kI8Tile;   // this tile's 128 columns: multipliers and biases
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail + kI8SigBytes + 2 * kI8Tile * 4);
     uint64_t *full_bar = bars, *empty_bar = bars + kI8Stages, *tmem_full = bars + 2 * kI8Stages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kI8Stages + 1);
 
@@ -129,8 +130,16 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (MODE != kI8Enc && warp < 4)
-        for (int i = tid; i <= kI8SigN; i += 128) s_sig[i] = __ldg(args.sig + i);
+    if (warp < 4) {
+        if (MODE != kI8Enc)
+            for (int i = tid; i <= kI8SigN; i += 128) s_sig[i] = __ldg(args.sig + i);
+        // column c of the tile: output tile * 128 + c (encoder / decoder), or gate c / 32 of unit tile * 32 + c % 32 (GRU: n_x | r | z | n_h,
+        // stored [4][H] in the order r, z, n_x, n_h)
+        const int gate = tid >> 5, slot = gate == 0 ? 2 : gate == 1 ? 0 : gate == 2 ? 1 : 3;
+        const int idx = MODE == kI8Gru ? slot * args.H + tile * kI8Units + (tid & 31) : tile * kI8Tile + tid;
+        s_mult[tid] = __ldg(args.mult + idx);
+        s_bias[tid] = __ldg(args.bias + idx);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
                 const int n = tile * kI8Tile + c;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    acc[i] = min(max(i8_requant(acc[i], __ldg(args.mult + n + i)) + __ldg(args.bias + n + i), 0), 32767);   // saturating relu, Q12
+                    acc[i] = min(max(i8_requant(acc[i], s_mult[c + i]) + s_bias[c + i], 0), 32767);   // saturating relu, Q12
                 i8_store_planes(out_row, H, n, acc);
             }
         } else if (MODE == kI8Dec) {
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
                 const int n = tile * kI8Tile + c;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    m[i] = (float) i8_sig(s_sig, i8_requant(acc[i], __ldg(args.mult + n + i)) + __ldg(args.bias + n + i)) * (1.0f / 32768.0f);
+                    m[i] = (float) i8_sig(s_sig, i8_requant(acc[i], s_mult[c + i]) + s_bias[c + i]) * (1.0f / 32768.0f);
                 *reinterpret_cast<float4 *>(mask_row + n) = make_float4(m[0], m[1], m[2], m[3]);
                 *reinterpret_cast<float4 *>(mask_row + n + 4) = make_float4(m[4], m[5], m[6], m[7]);
             }
@@ -219,10 +228,10 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
                 for (int i = 0; i < 8; ++i) {
                     const uint32_t hw = i < 4 ? ph.x : ph.y, lw = i < 4 ? pl.x : pl.y;
                     const int32_t hq = (int32_t) (int8_t) (hw >> (8 * (i & 3))) * 256 + (int32_t) ((lw >> (8 * (i & 3))) & 255u);
-                    const int32_t r = i8_sig(s_sig, i8_requant(ar[i], __ldg(args.mult + u + i)) + __ldg(args.bias + u + i));
-                    const int32_t z = i8_sig(s_sig, i8_requant(az[i], __ldg(args.mult + H + u + i)) + __ldg(args.bias + H + u + i));
-                    const int32_t pnx = i8_requant(anx[i], __ldg(args.mult + 2 * H + u + i)) + __ldg(args.bias + 2 * H + u + i);
-                    const int32_t pnh = i8_requant(anh[i], __ldg(args.mult + 3 * H + u + i)) + __ldg(args.bias + 3 * H + u + i);
+                    const int32_t r = i8_sig(s_sig, i8_requant(ar[i], s_mult[kI8Units + cu + i]) + s_bias[kI8Units + cu + i]);
+                    const int32_t z = i8_sig(s_sig, i8_requant(az[i], s_mult[2 * kI8Units + cu + i]) + s_bias[2 * kI8Units + cu + i]);
+                    const int32_t pnx = i8_requant(anx[i], s_mult[cu + i]) + s_bias[cu + i];
+                    const int32_t pnh = i8_requant(anh[i], s_mult[3 * kI8Units + cu + i]) + s_bias[3 * kI8Units + cu + i];
                     const int32_t a = pnx + (int32_t) (((long long) r * pnh + (1 << 14)) >> 15);
                     const int32_t nn = i8_tanh(s_sig, a);
                     const int32_t hn = nn + (int32_t) (((long long) z * (hq - nn) + (1 << 14)) >> 15);

@@ -124,15 +124,25 @@ def test_other_model_shapes(library_path, tmp_path, hidden, layers, precision):
 def test_long_host_call_layouts_agree(library_path, random_model_path):
     """A 140-frame host call exercises the ingest pipeline's output blocks (32-frame blocks, a short last block, a 4-frame last
     chunk); the time-major entry point (host and device buffers) and frame-by-frame calls must give the same samples."""
+    import os
     import torch
     n, frames = 6, 140
     pcm = synth_pcm(n, frames, seed=5)
     eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
-    whole = eng.process(pcm).copy()
+    whole = eng.process(pcm).copy()          # few streams: the ingest path scales its chunks up to 64 frames (64 + 64 + 12)
     eng.reset()
     stepped = np.stack([eng.process(np.ascontiguousarray(pcm[:, t, :])) for t in range(frames)], axis=1)
     assert (stepped == whole).all()
     tm = np.ascontiguousarray(pcm.transpose(1, 0, 2))
+    for chunk in ("8", "4"):                  # the chunk sizes a big batch gets: 8-frame input chunks in 32-frame output blocks; 4-frame time-major chunks
+        os.environ["KOALA_HOST_CHUNK"] = chunk
+        try:
+            eng.reset()
+            assert (eng.process(pcm) == whole).all(), chunk
+            eng.reset()
+            assert (eng.process(tm, time_major=True).transpose(1, 0, 2) == whole).all(), chunk
+        finally:
+            del os.environ["KOALA_HOST_CHUNK"]
     eng.reset()
     assert (eng.process(tm, time_major=True).transpose(1, 0, 2) == whole).all()
     eng.reset()
