@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: streams per GPU, precision, frames per process() call, description
-    "cfg4_8192_per_gpu_bf16": dict(streams=8192, precision="bf16", frames_per_call=16, time_major=True,
+    "cfg4_8192_per_gpu_bf16": dict(streams=8192, precision="bf16", frames_per_call=32, time_major=True,
                                    desc="BASELINE configs[3] per-GPU partition: 8192 concurrent 16 kHz streams/GPU, bf16 tcgen05 mask estimator"),
     "cfg3_4096_bf16": dict(streams=4096, precision="bf16", frames_per_call=32, time_major=True,
                            desc="BASELINE configs[2]: 4096 concurrent streams, 1xB200, bf16 tensor-core mask-estimator GEMMs"),
@@ -416,7 +416,10 @@ def roofline_of(name, streams, precision, prof, prof_steps, timed_seconds, peaks
     if precision == "int8":      # integer tensor pipe: no measured peak in MEASURED_PEAKS.json to divide by
         peak, src = None, "no measured int8 tensor peak available (MEASURED_PEAKS.json has bf16 only); achieved is in Tera integer op/s"
     traffic, traffic_src = ncu_traffic(name) if streams == WORKLOADS[name]["streams"] else (None, "stream count overridden")
-    kernel = ("tc_fused_kernel (encoder + GRU layers + decoder GEMMs, all streams" + ("" if prof_steps == dom_n else f", {prof_steps // max(dom_n, 1)} steps per launch") +
+    parts = -(-streams // 4096) if (fused and streams > 4096) else 1      # engine.cu kPartStreams: big batches run as partitions that fit the L2
+    per_launch = prof_steps * parts // max(dom_n, 1)
+    kernel = ("tc_fused_kernel (encoder + GRU layers + decoder GEMMs, " + (f"one of {parts} partitions of {streams // parts} streams" if parts > 1 else "all streams") +
+              ("" if per_launch == 1 else f", {per_launch} steps per launch") +
               (", fp32 operands as three bf16 planes: 3x the algorithmic flops are executed" if precision == "fp32" else "") + ")") if fused \
         else ("i8_layer_kernel<GRU> (one GRU layer, tcgen05 kind::i8, hi and lo byte planes: 2x the algorithmic multiply-adds are executed, "
               "plus a quarter of zero rows)" if precision == "int8" else "gru_fp32_kernel (CUDA-core FMA GRU layer)")

@@ -108,6 +108,12 @@ Status load_model_file(const char *path, ModelHost *out, std::vector<std::string
 }
 
 // ------------------------------------------------------------------------------------------------ engine
+// Batches larger than this many streams are run as PARTITIONS of at most this size, one after the other inside every chunk: a
+// partition's state and scratch (34 MB + the chunk's features / spectra / masks at 4096 streams) then stay in the 126 MB L2 for the
+// three launches of its chunk.  Measured per frame of all streams (r02r): 8192 streams 75.8 us as one batch, 2 x 34.9 as two
+// partitions; 16 384 streams 160.4 vs 4 x 34.9; 2048-stream partitions are slower again (19.6 us each).  KOALA_PARTITION_STREAMS
+// overrides (0: never partition).
+constexpr int kPartStreams = 4096;
 constexpr int kHostRing = 3;           // device input staging buffers of the host ingest path
 constexpr int kHostOutRing = 2;        // device output staging buffers (blocks)
 constexpr int kHostChunkFrames = 8;    // frames per input chunk
@@ -156,6 +162,10 @@ struct Engine::Impl {
     cudaStream_t last_stream = nullptr;
     bool has_last = false;
     cudaEvent_t ev_order = nullptr;
+    // A big batch is a composite: `parts` are engines of <= kPartStreams streams each (streams part_first[k] ..), which own all
+    // device state; the composite keeps only the host ingest path's streams and staging buffers.
+    std::vector<Engine *> parts;
+    std::vector<int> part_first;
 };
 
 // Makes `st` wait for everything enqueued so far on `prev` (falls back to a device synchronisation if `prev` is no longer a
@@ -253,6 +263,34 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
     p->H = (int) H;
     p->L = (int) L;
     p->num_sms = prop.multiProcessorCount;
+    {
+        const char *pe = getenv("KOALA_PARTITION_STREAMS");
+        const int part = pe ? std::max(0, atoi(pe)) / 256 * 256 : kPartStreams;
+        const char *cc = getenv("KOALA_FP32_CUDA_CORES");
+        const bool tensor_path = precision == kBf16 || (precision == kFp32 && H % 256 == 0 && !(cc && cc[0] == '1'));
+        if (tensor_path && part > 0 && num_streams > part) {
+            Status st = [&]() -> Status {
+                KCHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+                return kSuccess;
+            }();
+            p->tcap = 1 << 30;
+            for (int s0 = 0; s0 < num_streams && st == kSuccess; s0 += part) {
+                Engine *sub = nullptr;
+                st = Engine::create(model, device, std::min(part, num_streams - s0), precision, &sub, errors);
+                if (st == kSuccess) {
+                    p->parts.push_back(sub);
+                    p->part_first.push_back(s0);
+                    p->tcap = std::min(p->tcap, sub->chunk_frames());
+                }
+            }
+            if (st != kSuccess) {
+                delete eng;
+                return st;
+            }
+            *out = eng;
+            return kSuccess;
+        }
+    }
     if (const char *e = getenv("KOALA_STFT_PER_WARP")) p->stft_per_warp = std::max(1, atoi(e));
     Status st = [&]() -> Status {
         KCHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
@@ -375,6 +413,7 @@ Status Engine::create(const ModelHost &model, int device, int num_streams, int p
 Engine::~Engine() {
     if (!p_) return;
     cudaSetDevice(device_);
+    for (Engine *sub : p_->parts) delete sub;
     if (p_->has_last && p_->last_stream != p_->stream) cudaDeviceSynchronize();   // work may still be queued on a caller's stream
     cudaGetLastError();
     if (p_->stream) cudaStreamSynchronize(p_->stream);
@@ -425,6 +464,20 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
     if (p->has_last) KCHECK(chain_streams(p->last_stream, st, &p->ev_order));
     p->last_stream = st;
     p->has_last = true;
+    if (!p->parts.empty()) {       // chunk by chunk, partition after partition
+        for (int t0 = 0; t0 < frames; t0 += p->tcap) {
+            const int tc = std::min(p->tcap, frames - t0);
+            for (size_t k = 0; k < p->parts.size(); k++) {
+                const long long s0 = p->part_first[k];
+                const Status r = p->parts[k]->process_device(pcm + s0 * stride + (long long) t0 * frame_stride, out + s0 * out_stride + (long long) t0 * out_frame_stride,
+                                                              tc, stride, stream_, errors, out_stride, frame_stride, out_frame_stride);
+                if (r != kSuccess) return r;
+            }
+        }
+        launches_ = 0;
+        for (Engine *sub : p->parts) launches_ += sub->kernel_launches();
+        return kSuccess;
+    }
     if (p->fu) KCHECK(serialize_fused_launches(device_, p, st, &p->ev_order));
     const int B = n_, Bp = npad_, H = p->H, L = p->L;
     const size_t LBH = (size_t) Bp * H;
@@ -538,13 +591,16 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
     static const int out_env = [] { const char *e = getenv("KOALA_HOST_OUT_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : kHostOutFrames; }();
     // Small batches: a chunk of a few frames is a few hundred KB and the call becomes bound by the host's per-chunk work (two copies,
     // three launches, four events: ~40 us) -- scale the chunk to ~4 MiB of PCM, up to what one fused launch walks (128 streams: 64 frames)
+    // ... but never so long that the call has fewer than ~4 chunks to overlap its copies with its compute
     const int by_bytes = (int) std::min<size_t>((size_t) std::max(p->tcap, 1), ((size_t) 4 << 20) / ((size_t) n_ * kFrame * sizeof(int16_t)));
-    const int chunk_frames = chunk_forced > 0 ? chunk_forced : std::max(time_major ? kHostChunkFramesTm : kHostChunkFrames, by_bytes);
+    const int base_chunk = time_major ? kHostChunkFramesTm : kHostChunkFrames;
+    const int chunk_frames = chunk_forced > 0 ? chunk_forced : std::max(base_chunk, std::min(by_bytes, std::max(base_chunk, frames / 4)));
     const int Tc = frames < chunk_frames ? frames : chunk_frames;                 // frames per input chunk
     const int per_block = (time_major || frames < kHostBlockMinFrames) ? 1 : std::max(1, std::min(out_env, frames) / Tc);   // input chunks per output block
     const int To = per_block * Tc;                                                // frames per output block
     // staging is sized for the layout's full chunk / block, not for this call's length: a short call must not make the next long one reallocate
-    const int need_in = chunk_frames, need_out = std::max(To, (time_major ? 1 : std::max(1, out_env / chunk_frames)) * chunk_frames);
+    const int full_chunk = chunk_forced > 0 ? chunk_forced : std::max(base_chunk, by_bytes);
+    const int need_in = full_chunk, need_out = std::max(To, (time_major ? 1 : std::max(1, out_env / full_chunk)) * full_chunk);
     if ((size_t) need_in > p->staging_frames || (size_t) need_out > p->staging_out_frames) {
         for (int i = 0; i < kHostRing; i++) {
             if (p->d_in[i]) cudaFree(p->d_in[i]);
@@ -645,6 +701,35 @@ __global__ void reset_streams_kernel(const int32_t *__restrict__ ids, int n_ids,
 Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> *errors) {
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
+    if (!p->parts.empty()) {
+        if (stream_ids) {
+            if (n < 0) {
+                if (errors) errors->push_back("Negative stream count.");
+                return kInvalidArgument;
+            }
+            for (int i = 0; i < n; i++)
+                if (stream_ids[i] < 0 || stream_ids[i] >= n_) {
+                    if (errors) errors->push_back("Stream id out of range.");
+                    return kInvalidArgument;
+                }
+        }
+        for (size_t k = 0; k < p->parts.size(); k++) {
+            Engine *sub = p->parts[k];
+            if (!stream_ids) {
+                const Status r = sub->reset(nullptr, 0, errors);
+                if (r != kSuccess) return r;
+                continue;
+            }
+            std::vector<int32_t> local;
+            for (int i = 0; i < n; i++)
+                if (stream_ids[i] >= p->part_first[k] && stream_ids[i] < p->part_first[k] + sub->num_streams()) local.push_back(stream_ids[i] - p->part_first[k]);
+            if (!local.empty()) {
+                const Status r = sub->reset(local.data(), (int) local.size(), errors);
+                if (r != kSuccess) return r;
+            }
+        }
+        return kSuccess;
+    }
     const size_t Bp = npad_, H = p->H, L = p->L;
     // the state rows may still be in use by steps enqueued on a caller's stream (process_device): run after them
     if (p->has_last) KCHECK(chain_streams(p->last_stream, p->stream, &p->ev_order));
@@ -688,6 +773,8 @@ Status Engine::reset(const int32_t *stream_ids, int n, std::vector<std::string> 
 }
 
 void Engine::set_profile(bool on) {
+    for (Engine *sub : p_->parts) sub->set_profile(on);
+    if (!p_->parts.empty()) return;
     if (on && !p_->prof) p_->prof = new KernelProfiler();
     if (!on) {
         delete p_->prof;
@@ -696,6 +783,17 @@ void Engine::set_profile(bool on) {
 }
 
 Status Engine::profile_read(double *ms, long long *count, int n_classes, std::vector<std::string> *errors) {
+    if (!p_->parts.empty()) {
+        std::vector<double> m(std::max(n_classes, 0));
+        std::vector<long long> c(std::max(n_classes, 0));
+        for (int i = 0; i < n_classes; i++) { ms[i] = 0.0; count[i] = 0; }
+        for (Engine *sub : p_->parts) {
+            const Status r = sub->profile_read(m.data(), c.data(), n_classes, errors);
+            if (r != kSuccess) return r;
+            for (int i = 0; i < n_classes; i++) { ms[i] += m[i]; count[i] += c[i]; }
+        }
+        return kSuccess;
+    }
     if (n_classes < kKernClasses) {
         if (errors) errors->push_back("`num_classes` must be at least 6 (analysis, encoder, GRU, decoder, synthesis, fused mask estimator).");
         return kInvalidArgument;
@@ -723,6 +821,19 @@ Status Engine::synchronize(std::vector<std::string> *errors) {
 Status Engine::debug_read(const char *name, void *dst, size_t bytes, std::vector<std::string> *errors) {
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
+    if (!p->parts.empty()) {       // whole-batch reads only: every partition contributes its rows
+        if (name && std::string(name) == "trace") return p->parts[0]->debug_read(name, dst, bytes, errors);
+        if (bytes % (size_t) n_ != 0) {
+            if (errors) errors->push_back("A partitioned engine hands out whole tensors only (size must be a multiple of the stream count).");
+            return kInvalidArgument;
+        }
+        const size_t row = bytes / (size_t) n_;
+        for (size_t k = 0; k < p->parts.size(); k++) {
+            const Status r = p->parts[k]->debug_read(name, (uint8_t *) dst + (size_t) p->part_first[k] * row, (size_t) p->parts[k]->num_streams() * row, errors);
+            if (r != kSuccess) return r;
+        }
+        return kSuccess;
+    }
     KCHECK(cudaDeviceSynchronize());
     const size_t B = n_, Bp = npad_, H = p->H;
     const void *src = nullptr;

@@ -126,10 +126,10 @@ def test_both_part_orders_agree_with_the_oracle(library_path, random_model_path)
 
 
 def test_full_size_chunk_boundary(library_path, random_model_path):
-    """8192 streams x 20 frames in one call (default chunk = 16 frames: one boundary): replicas bit-identical, silent streams
-    silent, equal to the one-frame-per-call drive of a second engine, oracle spot check."""
+    """8192 streams x 40 frames in one call (two partitions of 4096 streams, chunks of 32 frames: one boundary): replicas
+    bit-identical, silent streams silent, equal to the one-frame-per-call drive of a second engine, oracle spot check."""
     import torch
-    n, frames = 8192, 20
+    n, frames = 8192, 40
     base = synth_pcm(64, frames, seed=19)
     pcm = np.tile(base, (n // 64, 1, 1))
     pcm[5::64] = 0
@@ -193,3 +193,36 @@ def test_fp32_hidden_size_outside_the_fused_tiles(library_path, tmp_path):
     eng.delete()
     with pytest.raises(kb.KoalaError):
         kb.BatchKoala(n, model_path=path, precision="bf16")
+
+
+def test_partitioned_batch_equals_one_batch(library_path, random_model_path):
+    """A batch above 4096 streams runs as partitions of 4096 (engine.cu kPartStreams) so that each partition's working set stays in
+    the L2.  Partitioning must be invisible: 600 streams as partitions of 256 (a ragged last one) == the same 600 streams as one
+    batch, bit for bit, through host and device buffers, with state carry, whole and per-stream reset and the state read-back."""
+    import torch
+    n, frames = 600, 21
+    pcm = synth_pcm(n, frames, seed=4096)
+    one = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    ref = one.process(pcm)
+    ref_h = [one.debug_read(f"h{l}", (n, 512), np.float32) for l in range(2)]
+    with env(KOALA_PARTITION_STREAMS=256):
+        eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    assert (eng.process(pcm) == ref).all()
+    assert eng.kernel_launches % 9 == 0                       # three partitions x three launches per chunk
+    for l in range(2):
+        assert (eng.debug_read(f"h{l}", (n, 512), np.float32) == ref_h[l]).all()
+    eng.reset()
+    halves = np.concatenate([eng.process(np.ascontiguousarray(pcm[:, :10])), eng.process(np.ascontiguousarray(pcm[:, 10:]))], axis=1)
+    assert (halves == ref).all()                               # state carried across calls in every partition
+    eng.reset()
+    tm = torch.from_numpy(np.ascontiguousarray(pcm.transpose(1, 0, 2))).cuda()
+    assert (eng.process(tm, time_major=True).cpu().numpy().transpose(1, 0, 2) == ref).all()
+    eng.reset([3, 300, 599])                                   # one stream in each partition restarts, the others carry on
+    cont, cont_ref = eng.process(pcm), None
+    one.reset([3, 300, 599])
+    cont_ref = one.process(pcm)
+    assert (cont == cont_ref).all() and (cont[[3, 300, 599]] == ref[[3, 300, 599]]).all()
+    with pytest.raises(kb.KoalaInvalidArgumentError):
+        eng.reset([600])
+    eng.delete()
+    one.delete()

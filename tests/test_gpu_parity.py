@@ -204,7 +204,8 @@ def test_device_tensors_and_full_size_properties(library_path, random_model_path
     _, ref = run_oracle(random_model_path, "bf16", np.ascontiguousarray(pcm[pick]))
     assert np.abs(out[pick].astype(np.int32) - ref.astype(np.int32)).max() <= LSB_TOL
     host = eng.process(pcm) if False else None                                    # host path covered elsewhere
-    assert eng.kernel_launches == 3 * ((frames + eng.chunk_frames - 1) // eng.chunk_frames)   # analysis, fused mask estimator, synthesis per chunk
+    # analysis, fused mask estimator, synthesis per chunk and per partition (batches above 4096 streams run as 4096-stream partitions)
+    assert eng.kernel_launches == 3 * 2 * ((frames + eng.chunk_frames - 1) // eng.chunk_frames)
     eng.delete()
 
 
