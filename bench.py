@@ -518,7 +518,7 @@ def main():
     sampler.start()
     ms_local, launches_local, calls_local, clocks = run.timed(args.steps, args.warmup, sampler)
     prof_steps = min(args.steps, 128) // w["frames_per_call"] * w["frames_per_call"] or min(args.steps, 128)
-    prof = run.profile(args.warmup + args.steps, prof_steps)
+    prof = run.profile(-(-(args.warmup + args.steps) // args.ring_frames) * args.ring_frames, prof_steps)     # starts at a ring boundary: whole calls only
     one_frame = None
     if w["frames_per_call"] > 1:        # the same steps driven one frame per call (three launches per frame)
         fpc, run.fpc = run.fpc, 1
@@ -566,7 +566,7 @@ def main():
                     o_steps = ow["steps"]        # the config's own length (configs[4]: a 10-minute clip per stream)
                 o_ms, o_launches, o_calls, _ = r.timed(o_steps, max(args.warmup, ow["frames_per_call"]))
                 o_prof_steps = max(ow["frames_per_call"], 64)
-                o_prof = r.profile(o_steps, o_prof_steps)
+                o_prof = r.profile(-(-o_steps // args.ring_frames) * args.ring_frames, o_prof_steps)
                 o_e2e = r.e2e(max(8, min(e2e_steps, 64)), extras=False)
                 o_value = ow["streams"] * o_steps / (o_ms * 1e-3)
                 roof = roofline_of(name, ow["streams"], ow["precision"], o_prof, o_prof_steps, o_ms * 1e-3, peaks)
