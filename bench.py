@@ -581,6 +581,27 @@ def main():
             except Exception as e:      # a side workload must never take the headline line down
                 others[name] = {"error": repr(e)[:300]}
 
+    if others is not None:
+        # BASELINE configs[0]: ONE stream through the reference-shaped per-frame API (create / process / delete), the fixture WAV's length
+        try:
+            import koala_b200 as kb
+            k = kb.create(access_key=kb.ANY_ACCESS_KEY, device=f"gpu:{local_rank}")
+            frame = [int(v) for v in synth_pcm(1, 1, 7)[0, 0]]
+            for _ in range(20):
+                k.process(frame)
+            t0 = time.perf_counter()
+            for _ in range(365):
+                k.process(frame)
+            dt = time.perf_counter() - t0
+            k.delete()
+            others["cfg1_single_stream_api"] = {
+                "description": "BASELINE configs[0] shape: one stream, koala_b200.create(...).process(frame) per 256-sample frame (Python list in, list out; "
+                               "H2D, three launches, D2H and a synchronisation per call), 365 frames = the fixture WAV's length, shipped weights",
+                "value": 365 / dt, "unit": "frames/s", "us_per_call": dt / 365 * 1e6, "rtf_x": 365 / dt * 0.016, "dtype": "bf16",
+                "note": "latency of one call, not throughput; the reference's CI floor for its CPU engine is 456 frames/s (BASELINE.md section 1)"}
+        except Exception as e:
+            others["cfg1_single_stream_api"] = {"error": repr(e)[:300]}
+
     if rank == 0:
         roofline = roofline_of(args.workload, streams, precision, prof, prof_steps, ms * 1e-3, peaks)
         step_prof_ms = sum(v[0] for v in prof.values()) / max(prof_steps, 1)
