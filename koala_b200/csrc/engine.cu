@@ -438,13 +438,37 @@ Engine::~Engine() {
     delete p_;
 }
 
-// STFT launches: warps walk a fixed number of items each; with items / resident warps rounded DOWN the grid is slightly larger
-// than what fits at once (kStftCtasPerSm CTAs of kStftWarps warps per SM) and its CTAs are short, which lets the next
-// kernel of the programmatic-dependent-launch chain move in earlier (8192 streams: 2 per warp, 82.4 vs 83.6 us per step)
+// STFT launches: the grid's warps walk the launch's items with a grid stride.
+// * Many items per warp (the chunked launches: 4096 streams x 32 frames = 37 per resident warp): exactly ONE wave of CTAs, so
+//   every warp gets the same count to within one.  With the count rounded down the grid was 911 CTAs where 888 fit at once, and the
+//   23 left over ran a second, almost empty wave as long as the first (frontend 5.15 -> 3.78 us per 4096-stream frame, r02x).
+// * A few items per warp (one frame per launch): items / resident warps rounded DOWN, i.e. a grid slightly larger than what fits at
+//   once, whose CTAs are short and let the next kernel of the programmatic-dependent-launch chain move in earlier (8192 streams:
+//   2 per warp, 82.4 vs 83.6 us per step).
 static int stft_grid_for(int items, int num_sms, int per_warp_override) {
-    const int resident_warps = num_sms * kStftCtasPerSm * kStftWarps;
+    const int resident_ctas = num_sms * kStftCtasPerSm, resident_warps = resident_ctas * kStftWarps;
+    if (per_warp_override <= 0 && items > 3 * resident_warps) return resident_ctas;
     const int per_warp = per_warp_override > 0 ? per_warp_override : std::max(1, items / resident_warps);
     return std::max(1, (items + kStftWarps * per_warp - 1) / (kStftWarps * per_warp));
+}
+
+// Synthesis of a chunk of `frames` frames of B streams: an item is a RUN of consecutive frames of one stream (the overlap-add half
+// stays in registers inside a run; a run that does not start the chunk re-synthesises the frame before it: one extra transform).
+// Picks the run length that minimises the transforms the busiest warp does -- ceil(items / resident warps) runs of run (+ 1)
+// transforms -- e.g. 4096 streams x 32 frames: 4 runs of 8 frames (5 items x 9 = 45 transforms per warp; 2 runs of 16 in a grid
+// of 1024 CTAs, as before, was two waves of 2 x 17 = 68).
+static int synthesis_run_for(int B, int frames, int num_sms) {
+    const long long resident_warps = (long long) num_sms * kStftCtasPerSm * kStftWarps;
+    int best_run = frames;
+    long long best_cost = -1;
+    for (int runs = 1; runs <= frames; runs++) {
+        const int run = (frames + runs - 1) / runs, actual = (frames + run - 1) / run;
+        if (actual != runs) continue;                       // the same run length as a smaller count: already seen
+        const long long items = (long long) B * actual, per_warp = std::max(1ll, (items + resident_warps - 1) / resident_warps);
+        const long long cost = per_warp * (run + (actual > 1 ? 1 : 0));
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_run = run; }
+    }
+    return best_run;
 }
 
 Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long long stride, void *stream_,
@@ -532,7 +556,6 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
         return kSuccess;
     }
     // tensor-core path: chunks of up to tcap frames, three launches per chunk chained with programmatic dependent launch
-    const int resident_warps = p->num_sms * kStftCtasPerSm * kStftWarps;
     for (int t0 = 0; t0 < frames; t0 += p->tcap) {
         const int tc = std::min(p->tcap, frames - t0);
         PcmView v{pcm, out, stride, out_stride, frame_stride, out_frame_stride, t0};
@@ -550,9 +573,7 @@ Status Engine::process_device(const int16_t *pcm, int16_t *out, int frames, long
         if (prof) { prof->end(st); prof->begin(kKernMasknet, st); }
         launches_ += 1 + fu_masknet_steps(p->fu, p->parity, tc, st);
         if (prof) { prof->end(st); prof->begin(kKernBackend, st); }
-        // synthesis runs: as long as the stream count allows while still filling the GPU about twice over
-        const int runs_wanted = (2 * resident_warps + B - 1) / B;
-        const int run = std::max(1, tc / runs_wanted), runs = (tc + run - 1) / run;
+        const int run = synthesis_run_for(B, tc, p->num_sms), runs = (tc + run - 1) / run;
         launch_pdl(true, backend_kernel, dim3(stft_grid_for(B * runs, p->num_sms, p->stft_per_warp)), dim3(kStftWarps * 32), 0, st, v, B, tc, run,
                    (long long) Bp, p->spec, p->mask, p->ola[p->ola_par], p->ola[p->ola_par ^ 1], p->tail, p->tables);
         if (prof) prof->end(st);
