@@ -119,7 +119,8 @@ constexpr int kHostOutRing = 2;        // device output staging buffers (blocks)
 constexpr int kHostChunkFrames = 8;    // frames per input chunk
 constexpr int kHostOutFrames = 32;     // frames per output block
 constexpr int kHostBlockMinFrames = 128;   // shorter calls send their output chunk by chunk
-constexpr int kHostChunkFramesTm = 4;  // frames per chunk of a time-major call
+constexpr int kHostChunkFramesTm = 4;  // frames per chunk of a time-major call (ramped schedules 1, 2, 4 .. 8 .. 4, 2, 1 and 1, 2, 4 .. 4 .. 2, 1 were
+                                       // tried for long calls of 8192 streams: 81.8 and 90.5 M frames/s against 91.4 M with uniform chunks, r02z)
 
 struct Engine::Impl {
     cudaStream_t stream = nullptr;

@@ -226,3 +226,20 @@ def test_partitioned_batch_equals_one_batch(library_path, random_model_path):
         eng.reset([600])
     eng.delete()
     one.delete()
+
+
+def test_long_time_major_host_call_of_a_big_batch(library_path, random_model_path):
+    """1100 streams x 75 frames from host memory in the time-major layout (7-frame chunks through the three-buffer input ring and the
+    two-buffer output ring, a ragged last chunk): what the same frames give from device memory, bit for bit, state carried into the
+    next call."""
+    import torch
+    n, frames = 1100, 75
+    pcm = synth_pcm(n, frames + 9, seed=1100)
+    tm = np.ascontiguousarray(pcm.transpose(1, 0, 2))
+    eng = kb.BatchKoala(n, model_path=random_model_path, precision="bf16")
+    ref = eng.process(torch.from_numpy(tm).cuda(), time_major=True).cpu().numpy()
+    eng.reset()
+    a = eng.process(tm[:frames], time_major=True)
+    b = eng.process(tm[frames:], time_major=True)
+    assert (a == ref[:frames]).all() and (b == ref[frames:]).all()
+    eng.delete()
