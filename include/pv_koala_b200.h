@@ -117,7 +117,11 @@ PV_API pv_status_t pv_koala_batch_process_async(pv_koala_batch_t *object, const 
  * base + s * stream_stride + t * frame_stride samples (time-major device buffers: stream_stride 256, frame_stride
  * num_streams * 256).  The call's frames are taken in chunks of up to pv_koala_batch_chunk_frames() frames: three kernel
  * launches per chunk (analysis of the chunk, one persistent mask-estimator launch walking its steps, synthesis), so the
- * caller's serial frame loop (reference: demo/c/koala_demo_file.c:466-521) costs launches per chunk, not per frame. */
+ * caller's serial frame loop (reference: demo/c/koala_demo_file.c:466-521) costs launches per chunk, not per frame.
+ * Handles of more than 4096 streams run every chunk as partitions of 4096 streams, one after the other (each partition's
+ * state then stays in the L2 for its chunk): three launches per partition and chunk; invisible otherwise.  Feed
+ * pv_koala_batch_chunk_frames() frames per call when they are available ("int8" handles and "fp32" handles whose hidden size is
+ * not a multiple of 256 work frame by frame: their chunk is 1). */
 PV_API pv_status_t pv_koala_batch_process_async_strided(pv_koala_batch_t *object, const int16_t *pcm, int16_t *enhanced_pcm,
                                                         int32_t num_frames, int64_t stream_stride, int64_t frame_stride, void *cuda_stream);
 PV_API pv_status_t pv_koala_batch_chunk_frames(const pv_koala_batch_t *object, int32_t *chunk_frames);
@@ -132,14 +136,15 @@ PV_API pv_status_t pv_koala_batch_delay_sample(const pv_koala_batch_t *object, i
 /* kernels launched so far by this handle (bench.py's gpu_launches) */
 PV_API pv_status_t pv_koala_batch_kernel_launches(const pv_koala_batch_t *object, int64_t *launches);
 /* Per-kernel-class CUDA-event timing on the launching stream.  SIX classes: 0 analysis/STFT, 1 encoder GEMM, 2 GRU layer,
- * 3 decoder GEMM, 4 synthesis/iSTFT (1-3: "fp32" handles), 5 fused mask estimator (encoder + GRU layers + decoder in one kernel,
- * "bf16" handles).  Enable, run steps, then read: read synchronises and returns summed milliseconds and launch counts per class
+ * 3 decoder GEMM, 4 synthesis/iSTFT (1-3: "int8" handles and the CUDA-core "fp32" path), 5 fused mask estimator (encoder + GRU
+ * layers + decoder in one kernel: "bf16" and "fp32" handles).  Enable, run steps, then read: read synchronises and returns summed milliseconds and launch counts per class
  * since the previous read; num_classes must be >= 6 (INVALID_ARGUMENT otherwise; INVALID_STATE if profiling is off).
  * Off by default (events perturb back-to-back launches). */
 PV_API pv_status_t pv_koala_batch_profile(pv_koala_batch_t *object, int32_t enable);
 PV_API pv_status_t pv_koala_batch_profile_read(pv_koala_batch_t *object, double *ms_per_class, int64_t *launches_per_class,
                                                int32_t num_classes);
-/* test hook: copy an internal tensor of the last step to the host: "feat" "spec" "mask" "e" "h0".."h7" "ola" "tail" */
+/* test hook: copy an internal tensor of the last step to the host: "feat" "spec" "mask" "e" "h0".."h7" "ola" "tail"
+ * ([num_streams][...] rows; "feat" / "e": fp32 for "fp32" handles, bf16 bits for "bf16", int16 for "int8"; "h*": fp32) */
 PV_API pv_status_t pv_koala_batch_debug_read(pv_koala_batch_t *object, const char *name, void *dst, int64_t bytes);
 
 #ifdef __cplusplus
