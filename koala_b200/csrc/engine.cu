@@ -148,6 +148,8 @@ struct Engine::Impl {
     // staging for host-buffer calls
     int16_t *d_in[kHostRing] = {}, *d_out[kHostOutRing] = {};   // [B][staging_frames][256] / [B][staging_out_frames][256] each
     size_t staging_frames = 0, staging_out_frames = 0;
+    int16_t *d_small = nullptr;  // in | out staging of calls small enough to be one chunk (process_host)
+    size_t small_samples = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[kHostRing] = {}, ev_comp[kHostRing] = {}, ev_out[kHostOutRing] = {};
     FuPlan *fu = nullptr;        // tcgen05 path: packed weights, tensor maps and the tile schedule of the fused mask-estimator kernel
@@ -433,6 +435,7 @@ Engine::~Engine() {
         if (p_->d_out[i]) cudaFree(p_->d_out[i]);
         if (p_->ev_out[i]) cudaEventDestroy(p_->ev_out[i]);
     }
+    if (p_->d_small) cudaFree(p_->d_small);
     if (p_->copy_in) cudaStreamDestroy(p_->copy_in);
     if (p_->copy_out) cudaStreamDestroy(p_->copy_out);
     if (p_->stream) cudaStreamDestroy(p_->stream);
@@ -610,6 +613,26 @@ Status Engine::process_host(const int16_t *pcm, int16_t *out, int frames, std::v
     Impl *p = p_;
     KCHECK(cudaSetDevice(device_));
     const int chunk_forced = [] { const char *e = getenv("KOALA_HOST_CHUNK"); return e ? std::max(0, atoi(e)) : 0; }();      // tests / tuning: exactly this many frames per input chunk
+    // A call that is one chunk anyway (the reference-shaped use: pv_koala_process, one frame of one stream) has nothing to overlap:
+    // copy in, step, copy out on the engine's own stream, one synchronisation -- no copy streams, no events (95 -> ~75 us per call).
+    if (chunk_forced <= 0 && (size_t) n_ * frames * kFrame * sizeof(int16_t) <= ((size_t) 64 << 10)) {
+        const size_t samples = (size_t) n_ * frames * kFrame;
+        if (samples > p->small_samples) {
+            if (p->d_small) cudaFree(p->d_small);
+            p->d_small = nullptr;
+            p->small_samples = 0;
+            KCHECK(cudaMalloc((void **) &p->d_small, 2 * samples * sizeof(int16_t)));
+            p->small_samples = samples;
+        }
+        int16_t *d_in = p->d_small, *d_out = p->d_small + p->small_samples;
+        KCHECK(cudaMemcpyAsync(d_in, pcm, samples * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
+        const Status st = time_major ? process_device(d_in, d_out, frames, kFrame, p->stream, errors, kFrame, (long long) n_ * kFrame, (long long) n_ * kFrame)
+                                     : process_device(d_in, d_out, frames, (long long) frames * kFrame, p->stream, errors);
+        if (st != kSuccess) return st;
+        KCHECK(cudaMemcpyAsync(out, d_out, samples * sizeof(int16_t), cudaMemcpyDeviceToHost, p->stream));
+        KCHECK(cudaStreamSynchronize(p->stream));
+        return kSuccess;
+    }
     static const int out_env = [] { const char *e = getenv("KOALA_HOST_OUT_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : kHostOutFrames; }();
     // Small batches: a chunk of a few frames is a few hundred KB and the call becomes bound by the host's per-chunk work (two copies,
     // three launches, four events: ~40 us) -- scale the chunk to ~4 MiB of PCM, up to what one fused launch walks (128 streams: 64 frames)
