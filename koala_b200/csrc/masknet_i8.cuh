@@ -15,7 +15,8 @@
 // saturation to int16.
 //
 // One kernel per layer and step (encoder, GRU layer, decoder), one 128-row x 128-column tile per CTA, cta_group::1:
-//   warps 0..3  epilogue (TMEM lane quarter = warp), warp 4 TMA producer, warp 5 TMEM allocation + MMA issuer;
+//   warps 0..7  epilogue (TMEM lane quarter = warp % 4, column half = warp / 4: the integer gate math is a long dependent chain
+//   with table lookups, so it wants warps), warp 8 TMA producer, warp 9 TMEM allocation + MMA issuer;
 //   2 stages of (A hi + A lo + B, each [128 rows][128 B]), 128B-swizzled, K-major.
 // GRU tile = 128 streams x 32 units, TMEM columns [n_x | r | z | n_h] x 32: the x part's weight rows are packed [n | r | z | 0]
 // and the h part's [0 | r | z | n] (zero rows instead of the bf16 kernel's column-offset trick: this path is built for parity
@@ -36,10 +37,11 @@ constexpr int kI8Stages = 2;
 constexpr int kI8Tile = 128;                              // rows per CTA, columns per tile, int8 per k-block
 constexpr int kI8TileBytes = kI8Tile * 128;
 constexpr int kI8StageBytes = 3 * kI8TileBytes;           // activations hi plane, activations lo plane, weights
-constexpr int kI8Threads = 192;
+constexpr int kI8EpiWarps = 8;                            // two per TMEM lane quarter, each taking half of the tile's columns
+constexpr int kI8Threads = 32 * (kI8EpiWarps + 2);
 constexpr int kI8Units = 32;                              // GRU units per tile
 constexpr int kI8SigN = 2048;                             // sigmoid table intervals over [-8, 8)
-constexpr int kI8SigBytes = (kI8SigN + 1) * 2 + 14;       // padded to 16 bytes
+constexpr int kI8SigBytes = kI8SigN * 4;                  // device copy: entry i = T[i] | (T[i + 1] - T[i]) << 16, one 32-bit lookup per interpolation
 constexpr int kI8SmemBytes = 1024 + kI8Stages * kI8StageBytes + kI8SigBytes + 2 * kI8Tile * 4 + 128;
 constexpr int kQF = 14, kQE = 12, kQH = 15, kQP = 12;     // Q formats: features, encoder output, state, pre-activations
 
@@ -50,7 +52,7 @@ struct I8Args {
     int kb_x, kb_h;                   // k-blocks of 128 per plane and part
     int k_x, H;                       // columns of one plane of the x operand; hidden size
     const int32_t *mult, *bias;       // encoder / decoder: [N]; GRU: [4][H] = r, z, n_x, n_h
-    const int16_t *sig;               // [kI8SigN + 1]
+    const uint32_t *sig;              // [kI8SigN] packed sigmoid table: T[i] | (T[i + 1] - T[i]) << 16
     const uint8_t *h_prev;            // GRU: planes of h(t-1), [rows][2 H]
     uint8_t *out_planes;              // encoder: planes of e; GRU: planes of h(t)
     float *mask;                      // decoder: [rows][256]
@@ -79,13 +81,13 @@ __device__ __forceinline__ void tmem_ld8_i32(uint32_t taddr, int32_t (&v)[8]) {
 
 // SPEC.md section 6 integer helpers (the same expressions as oracle/koala_oracle.c)
 __device__ __forceinline__ int32_t i8_requant(int32_t acc, int32_t mult) { return (int32_t) (((long long) acc * mult + (1ll << 30)) >> 31); }
-__device__ __forceinline__ int32_t i8_sig(const int16_t *t, int32_t p) {
+__device__ __forceinline__ int32_t i8_sig(const uint32_t *t, int32_t p) {
     const int32_t x = min(max(p, -32768), 32767) + 32768;
     const int32_t i = x >> 5, f = x & 31;
-    const int32_t a = t[i], b = t[i + 1];
-    return a + (((b - a) * f + 16) >> 5);
+    const uint32_t e = t[i];                                   // T[i] and the step to T[i + 1] (0 .. 64)
+    return (int32_t) (e & 0xffffu) + (((int32_t) (e >> 16) * f + 16) >> 5);
 }
-__device__ __forceinline__ int32_t i8_tanh(const int16_t *t, int32_t a) { return 2 * i8_sig(t, a < -16384 ? -32768 : a > 16383 ? 32767 : 2 * a) - 32768; }
+__device__ __forceinline__ int32_t i8_tanh(const uint32_t *t, int32_t a) { return 2 * i8_sig(t, a < -16384 ? -32768 : a > 16383 ? 32767 : 2 * a) - 32768; }
 // the 8 combined accumulators of one gate: columns col .. col + 7 of both planes
 __device__ __forceinline__ void i8_load_acc(uint32_t lane_base, int col, int32_t (&acc)[8]) {
     int32_t hi[8], lo[8];
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
     extern __shared__ uint8_t i8_smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 1023) & ~(uintptr_t) 1023);
     uint8_t *tail = smem + kI8Stages * kI8StageBytes;
-    int16_t *s_sig = reinterpret_cast<int16_t *>(tail);
+    uint32_t *s_sig = reinterpret_cast<uint32_t *>(tail);
     int32_t *s_mult = reinterpret_cast<int32_t *>(tail + kI8SigBytes), *s_bias = s_mult + kI8Tile;   // this tile's 128 columns: multipliers and biases
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail + kI8SigBytes + 2 * kI8Tile * 4);
     uint64_t *full_bar = bars, *empty_bar = bars + kI8Stages, *tmem_full = bars + 2 * kI8Stages;
@@ -127,19 +129,21 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
         mbar_init(tmem_full, 1);
         fence_mbar_init();
     }
-    if (warp == 5) {
+    if (warp == kI8EpiWarps + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp < 4) {
+    if (warp < kI8EpiWarps) {
         if (MODE != kI8Enc)
-            for (int i = tid; i <= kI8SigN; i += 128) s_sig[i] = __ldg(args.sig + i);
+            for (int i = tid; i < kI8SigN / 4; i += 32 * kI8EpiWarps) reinterpret_cast<uint4 *>(s_sig)[i] = __ldg(reinterpret_cast<const uint4 *>(args.sig) + i);
         // column c of the tile: output tile * 128 + c (encoder / decoder), or gate c / 32 of unit tile * 32 + c % 32 (GRU: n_x | r | z | n_h,
         // stored [4][H] in the order r, z, n_x, n_h)
         const int gate = tid >> 5, slot = gate == 0 ? 2 : gate == 1 ? 0 : gate == 2 ? 1 : 3;
         const int idx = MODE == kI8Gru ? slot * args.H + tile * kI8Units + (tid & 31) : tile * kI8Tile + tid;
-        s_mult[tid] = __ldg(args.mult + idx);
-        s_bias[tid] = __ldg(args.bias + idx);
+        if (tid < kI8Tile) {
+            s_mult[tid] = __ldg(args.mult + idx);
+            s_bias[tid] = __ldg(args.bias + idx);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
     const uint32_t tmem_base = *tmem_slot;
     const int total = args.kb_x + args.kb_h;          // k-blocks: x part, then (GRU) h part
 
-    if (warp == 4) {
+    if (warp == kI8EpiWarps) {
         // ===================================================== TMA producer: both activation planes and the weights of a k-block
         if (elect_one()) {
             for (int i = 0; i < total; ++i) {
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == kI8EpiWarps + 1) {
         // ===================================================== MMA issuer
         if (elect_one()) {
             const uint64_t adesc0 = make_sw128_desc(smem_u32(smem)), bdesc0 = make_sw128_desc(smem_u32(smem) + 2 * kI8TileBytes);
@@ -188,14 +192,15 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
         __syncwarp();
     } else {
         // ===================================================== epilogue: thread = stream row = TMEM lane
-        const size_t row = (size_t) m0 + tid;
-        const uint32_t lane_base = tmem_base + ((uint32_t) (warp * 32) << 16);
+        const int quarter = warp & 3, half = warp >> 2;
+        const size_t row = (size_t) m0 + quarter * 32 + (tid & 31);
+        const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
         const int H = args.H;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         if (MODE == kI8Enc) {
             uint8_t *out_row = args.out_planes + row * 2 * H;
-            for (int c = 0; c < kI8Tile; c += 8) {
+            for (int c = half * (kI8Tile / 2); c < (half + 1) * (kI8Tile / 2); c += 8) {
                 int32_t acc[8];
                 i8_load_acc(lane_base, c, acc);
                 const int n = tile * kI8Tile + c;
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
             }
         } else if (MODE == kI8Dec) {
             float *mask_row = args.mask + row * kBins;
-            for (int c = 0; c < kI8Tile; c += 8) {
+            for (int c = half * (kI8Tile / 2); c < (half + 1) * (kI8Tile / 2); c += 8) {
                 int32_t acc[8];
                 float m[8];
                 i8_load_acc(lane_base, c, acc);
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
         } else {
             const uint8_t *prev_row = args.h_prev + row * 2 * H;
             uint8_t *out_row = args.out_planes + row * 2 * H;
-            for (int cu = 0; cu < kI8Units; cu += 8) {
+            for (int cu = half * (kI8Units / 2); cu < (half + 1) * (kI8Units / 2); cu += 8) {
                 int32_t anx[8], ar[8], az[8], anh[8], out[8];
                 i8_load_acc(lane_base, cu, anx);
                 i8_load_acc(lane_base, kI8Units + cu, ar);
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(kI8Threads) i8_layer_kernel(const __grid_const
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kI8EpiWarps + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
     }
@@ -394,7 +399,9 @@ static bool i8_plan_create(const ModelHost &model, int Bp, float *mask, I8Plan *
     const int8_t *dec_q = (const int8_t *) put(q.dec_q.data(), q.dec_q.size());
     const int32_t *enc_m = (const int32_t *) put(q.enc_m.data(), 4 * q.enc_m.size()), *enc_b = (const int32_t *) put(q.enc_b.data(), 4 * q.enc_b.size());
     const int32_t *dec_m = (const int32_t *) put(q.dec_m.data(), 4 * q.dec_m.size()), *dec_b = (const int32_t *) put(q.dec_b.data(), 4 * q.dec_b.size());
-    const int16_t *sig = (const int16_t *) put(q.sig.data(), 2 * q.sig.size());
+    std::vector<uint32_t> packed_sig(kI8SigN);
+    for (int i = 0; i < kI8SigN; i++) packed_sig[i] = (uint32_t) (uint16_t) q.sig[i] | ((uint32_t) (q.sig[i + 1] - q.sig[i]) << 16);
+    const uint32_t *sig = (const uint32_t *) put(packed_sig.data(), 4 * packed_sig.size());
     const int8_t *wx[kMaxLayers] = {}, *wh[kMaxLayers] = {};
     const int32_t *gm[kMaxLayers] = {}, *gb[kMaxLayers] = {};
     for (size_t l = 0; l < L; l++) {
