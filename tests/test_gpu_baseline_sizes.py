@@ -153,3 +153,31 @@ def test_config5_shape_state_carry_in_chunks(library_path, shipped_model_path):
     first, last = d[:, :frames // 4], d[:, -frames // 4:]
     assert (last >= 1).mean() <= 2.0 * (first >= 1).mean() + 1e-3      # no drift: the end of the run looks like its beginning
     eng.delete()
+
+
+def test_every_stream_of_the_full_batch_against_oracle(library_path, random_model_path):
+    """The per-GPU partition of BASELINE configs[3] with NO sampling: all 8192 streams (distinct data, both 4096-stream partitions,
+    all 32 stream tiles) x 32 frames = 67 M samples compared with the oracle; +-1 LSB everywhere, histogram written out."""
+    n_streams, frames = 8192, 32
+    pcm = distinct_pcm(n_streams, frames, seed=81920)
+    eng = kb.BatchKoala(n_streams, model_path=random_model_path, precision="bf16")
+    out = eng.process(np.ascontiguousarray(pcm.transpose(1, 0, 2)), time_major=True).transpose(1, 0, 2)
+    eng.delete()
+    ref = OracleBatch(OracleModel(random_model_path), n_streams, "bf16").process(pcm, threads=os.cpu_count() or 8)
+    hist = lsb_histogram(out, ref)
+    dump("parity_hist_8192_bf16_every_stream.json", {"streams": n_streams, "precision": "bf16", "frames": frames, "compared_streams": n_streams, **hist})
+    assert hist["samples"] == n_streams * frames * 256 and hist["max"] <= 1, hist
+
+
+def test_every_stream_of_a_fixed_point_batch_against_oracle(library_path, random_model_path):
+    """Fixed-point mode at BASELINE configs[2] size: all 4096 streams x 16 frames against the oracle's mode 2 (+-1 LSB; the integer mask
+    network itself is compared for equality in tests/test_gpu_fixed_point.py)."""
+    n_streams, frames = 4096, 16
+    pcm = distinct_pcm(n_streams, frames, seed=40960)
+    eng = kb.BatchKoala(n_streams, model_path=random_model_path, precision="int8")
+    out = eng.process(pcm)
+    eng.delete()
+    ref = OracleBatch(OracleModel(random_model_path), n_streams, "int8").process(pcm, threads=os.cpu_count() or 8)
+    hist = lsb_histogram(out, ref)
+    dump("parity_hist_4096_int8_every_stream.json", {"streams": n_streams, "precision": "int8", "frames": frames, "compared_streams": n_streams, **hist})
+    assert hist["max"] <= 1, hist
