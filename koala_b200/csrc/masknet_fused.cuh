@@ -372,60 +372,58 @@ __global__ void __cluster_dims__(kFuCluster, 1, 1) __launch_bounds__(kFuThreads,
         }
     } else if (warp == 2) {
         // ===================================================== MMA issuer (one thread of the leader CTA drives both SMs)
-        if (rank == 0) {
-            int it = 0;
-            unsigned kb_total = 0;           // k-blocks issued so far: every lane derives the pipeline position from it
+        // The whole tile loop runs in ONE elected lane: every instruction between two k-blocks (barrier test, descriptor
+        // arithmetic, moves into uniform registers) and between two tiles (decoding the next tile: ~500 cycles of dependent
+        // constant-bank loads) is serial latency of this thread and shows up one-for-one as idle tensor-pipe time, so nothing
+        // is re-elected, re-synchronised or broadcast, the k loop is split by operand part to keep its body branch-free, and the
+        // NEXT tile is decoded right behind the first k-block of the current one, while its MMAs run (the r02j trace showed
+        // ~900 cycles between a tile's last MMA and the next tile's first with the decode at the top of the loop).
+        // GRU: the h part writes columns [r | z | n_h], the x part [n_x | r | z]; whichever runs first overwrites its columns,
+        // the other accumulates -- its private n columns were left zeroed by the epilogue.
+        if (rank == 0 && elect_one()) {
+            int it = 0, stage = 0, phase = 0;
             const uint64_t adesc0 = make_sw128_desc(smem_u32(smem)), bdesc0 = make_sw128_desc(smem_u32(smem) + kTcABytes);
             FuTile t, t_next;
             FuIter pos;
             fu_iter_init(args, pos, cluster_id);
-            bool have = fu_next(args, pos, num_clusters, t);
+            bool have = fu_next(args, pos, num_clusters, t), have_next = false;
             for (; have; ++it) {
                 const FuSeg &sg = args.seg[t.s];
                 const bool gru = sg.mode == kTcGru;
-                const int num_kb = sg.kb_per_part * sg.parts, kbp = sg.kb_per_part;
+                const int kbp = sg.kb_per_part, parts = sg.parts;
                 const uint32_t idesc = gru ? make_idesc(256, kGruRows) : make_idesc(256, kFuLinN);
                 const int hpart = gru ? (sg.x_first ? 1 : 0) : -1;
                 const int ab = it & 1, aphase = (it >> 1) & 1;
-                // the next tile is decoded here, in front of this tile's barrier waits, which absorb it: decoded after the k
-                // loop it was ~600 idle cycles of the tensor pipe per tile (r02d trace)
-                fu_iter_advance(args, pos, num_clusters);
-                have = fu_next(args, pos, num_clusters, t_next);
                 mbar_wait(&tmem_empty[ab], aphase);      // both CTAs' epilogues have released (and cleared) this buffer
                 tc_fence_after();
-                if (lane == 0) KTRACE(it, 2);
+                KTRACE(it, 2);
                 const uint32_t d = tmem_base + ab * kTcAccCols;
-                // The whole k loop runs in ONE elected lane: every instruction between two k-blocks (barrier test, descriptor
-                // arithmetic, moves into uniform registers) is serial latency of this thread and shows up one-for-one in the
-                // k-block time, so nothing is re-elected, re-synchronised or re-selected per k-block, and the loop is split by
-                // operand part to keep its body branch-free.  GRU: the h part writes columns [r | z | n_h], the x part
-                // [n_x | r | z]; whichever runs first overwrites its columns, the other accumulates -- its private n columns
-                // were left zeroed by the epilogue.
-                int stage = (int) (kb_total % kStages), phase = (int) ((kb_total / kStages) & 1);
-                kb_total += (unsigned) num_kb;
-                if (elect_one()) {
-                    for (int part = 0; part < sg.parts; ++part) {
-                        const uint32_t dk = part == hpart ? d + kGruUnits : d;
-                        const uint32_t first = part == 0 ? 0u : 1u;
-                        for (int kb = 0; kb < kbp; ++kb) {
-                            mbar_wait(&full_bar[stage], phase);
-                            tc_fence_after();
-                            KTRACE(it, 32 + part * kbp + kb);
-                            const uint64_t so = (uint64_t) ((stage * kStageBytes) >> 4);
+                for (int part = 0; part < parts; ++part) {
+                    const uint32_t dk = part == hpart ? d + kGruUnits : d;
+                    const uint32_t first = part == 0 ? 0u : 1u;
+                    for (int kb = 0; kb < kbp; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        KTRACE(it, 32 + part * kbp + kb);
+                        const uint64_t so = (uint64_t) ((stage * kStageBytes) >> 4);
 #pragma unroll
-                            for (int k = 0; k < kTcBlockK / 16; ++k)    // +32 B per 16-element k-step
-                                umma_bf16_pair(dk, adesc0 + so + 2 * k, bdesc0 + so + 2 * k, idesc, (kb | k) != 0 ? 1u : first);
-                            umma_commit_pair(&empty_bar[stage], pair_mask);
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        for (int k = 0; k < kTcBlockK / 16; ++k)    // +32 B per 16-element k-step
+                            umma_bf16_pair(dk, adesc0 + so + 2 * k, bdesc0 + so + 2 * k, idesc, (kb | k) != 0 ? 1u : first);
+                        umma_commit_pair(&empty_bar[stage], pair_mask);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if ((part | kb) == 0) {              // the tensor pipe has a k-block to chew on: find the next tile now
+                            fu_iter_advance(args, pos, num_clusters);
+                            have_next = fu_next(args, pos, num_clusters, t_next);
                         }
                     }
-                    umma_commit_pair(&tmem_full[ab], pair_mask);
                 }
-                __syncwarp();
-                if (lane == 0) KTRACE(it, 3);
+                umma_commit_pair(&tmem_full[ab], pair_mask);
+                KTRACE(it, 3);
                 t = t_next;
+                have = have_next;
             }
         }
+        __syncwarp();
     } else if (warp == kTcStateWarp) {
         // ===================================================== state warp: one thread moves the staging boxes of the GRU tiles
         // (two passes of 32 units each).  `cur` walks the passes in order (wait until staged, store fp32 + bf16 h(t), commit);
