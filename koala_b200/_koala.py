@@ -6,6 +6,7 @@ The hot call is `Koala.process` (_koala.py:224-254 in the reference): length che
 constructor raises.
 """
 import os
+from array import array
 from ctypes import CDLL, POINTER, Structure, byref, c_char_p, c_int, c_int32, c_short
 from enum import Enum
 from typing import Sequence
@@ -207,11 +208,14 @@ class Koala(object):
             raise KoalaInvalidArgumentError(
                 "Length of input frame %d does not match required frame length %d" % (len(pcm), self.frame_length))
         frame_type = c_short * self.frame_length
-        pcm = frame_type(*pcm)
+        try:
+            # same bytes as `frame_type(*pcm)` for in-range ints, 5x cheaper to build (the call itself is ~65 us)
+            frame = frame_type.from_buffer(array('h', pcm))
+        except (OverflowError, TypeError):
+            frame = frame_type(*pcm)       # whatever the reference binding's marshalling does with such input (wrap / raise)
         enhanced_pcm = frame_type()
-        check(self._library, self._process_func(self._handle, pcm, enhanced_pcm), 'Processing failed')
-        # noinspection PyTypeChecker
-        return list(enhanced_pcm)
+        check(self._library, self._process_func(self._handle, frame, enhanced_pcm), 'Processing failed')
+        return enhanced_pcm[:]
 
     def reset(self) -> None:
         """Resets Koala into a state as if it had just been newly created."""
