@@ -17,6 +17,17 @@ ANY_ACCESS_KEY = "a29hbGFfYjIwMF9uby1saWNlbmNlLXNlcnZlcg=="   # syntactically va
 
 
 class BatchKoala(object):
+    """`num_streams` independent 16 kHz streams on one B200 behind `pv_koala_batch_*` (include/pv_koala_b200.h, part 2); stream s keeps
+    the state a `Koala` handle would (/root/reference/binding/python/_koala.py:224-254 is the one-stream call this batches).
+
+    precision: "bf16" (tcgen05 mask estimator, bf16 operands), "fp32" (the same kernel, every activation as three bf16 planes) or
+    "int8" (fixed-point variant: int8 weights x int16 activations on the integer tensor cores; SPEC.md section 6).
+    `process(pcm)`: int16 `[num_streams][frames][256]` (or `[frames][num_streams][256]` with `time_major=True`), numpy / pinned
+    torch host tensors or CUDA tensors; state carries across calls.  Feed `chunk_frames` frames per call when they are available:
+    a call's frames are walked by one persistent mask-estimator launch per chunk (and per 4096-stream partition of a bigger batch).
+    A handle is not thread-safe; CUDA-tensor calls are enqueued on torch's current stream and ordered against earlier work on
+    other streams by the library."""
+
     class CBatch(Structure):
         pass
 
