@@ -106,9 +106,9 @@ def test_full_scale_inputs_residual_is_quantified(library_path, random_model_pat
     bf16 mode: both sides round every GEMM operand to bf16, but from fp32 values that differ in the last bits (summation
     order, FFT schedule, transcendental approximations), so now and then an operand lands on the other side of a bf16 rounding
     boundary (~0.5 per stream-step).  One such flip moves the mask by ~3e-5; carried through the recurrent state over 64 steps the
-    masks differ by up to ~2.5e-4 absolute -- well inside the 1e-3 mask tolerance, invisible (< 1 LSB) for |x| < ~4000 (every
-    BASELINE workload: max 1 LSB, 99.7 % exact, test above), but up to |x| * 2.5e-4 = 8 LSB at the rails.  Asserted bound:
-    |cuda - oracle| <= 1 + 2.5e-4 * 32768 = 9 LSB, and at most 1 LSB on at least 80 % of the samples."""
+    masks differ by up to ~3e-4 absolute -- well inside the 1e-3 mask tolerance, invisible (< 1 LSB) for |x| < ~3000 (the synthetic
+    BASELINE workloads: max 1 LSB, 99.7 % exact, test above), but up to 6 LSB measured at the rails.  SPEC.md section 4 states the
+    general bound 1 + 1e-3 |x|; asserted here, tighter: |cuda - oracle| <= 9 LSB, and at most 1 LSB on at least 80 % of the samples."""
     n, frames = 64, 64
     pcm = full_scale_pcm(n, frames)
     for precision, max_lsb in (("fp32", 1), ("bf16", 9)):

@@ -174,7 +174,7 @@ def test_edge_inputs(library_path, random_model_path, precision):
     else:
         # bf16 operands: GPU and oracle agree on the pre-rounding fp32 value to ~1e-6, so once in a while an operand
         # lands on the other side of a bf16 rounding boundary (2^-9 relative).  That moves the mask by ~3e-5, i.e. by
-        # 1 LSB at |x| = 32767 -- the only level where it can show.  Bound of SPEC.md section 4: 1 + 2.5e-4 |x| LSB, quantified over
+        # 1 LSB at |x| = 32767 -- the only level where it can show.  Bound of SPEC.md section 4: 1 + 1e-3 |x| LSB (measured: up to 6 LSB at the rails), quantified over
         # 10^6 samples in tests/test_gpu_baseline_sizes.py; after only 6 frames it is 2 LSB on under 10 % of the samples.
         assert diff.max() <= 2 and (diff > LSB_TOL).mean() < 0.10, (diff.max(), (diff > LSB_TOL).mean())
     assert eng.process(np.zeros((n, 0, 256), np.int16)).shape == (n, 0, 256)      # empty call is a no-op
